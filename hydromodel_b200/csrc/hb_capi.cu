@@ -1,0 +1,807 @@
+// hb_capi.cu -- kernels and the C-ABI (include/hydrob200.h) of libhydrob200.so.
+//
+// Kernels (all FP64, no tensor cores -- nothing here is a dense contraction):
+//   run_kernel      persistent CTAs pull columns from an atomic queue and run
+//                   the window loop of Simulation.run (simulation.py:576-649)
+//   spinup_kernel   Simulation.initial_conditions (simulation.py:444-480)
+//   hook_kernel     one CTA exposing RHS / closure / Jacobian / tridiagonal
+//                   solve / single window for the parity tests
+//   philox_base_kernel, moments_kernel   noise initialisation, ensemble stats
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/hydrob200.h"
+#ifndef HB_MIN_BLOCKS
+#define HB_MIN_BLOCKS 2
+#endif
+#include "hb_device.cuh"
+
+using namespace hb;
+
+template <int NT>
+__device__ inline void bind_column(const DevCtx &c, int col)
+{
+    for (int i = threadIdx.x; i < HB_NPARAM; i += NT)
+        HB_X(c, X_PAR)[i] = c.par[(size_t)col * HB_NPARAM + i];
+}
+
+__device__ inline void add_counters(long long *dst, const Counters &k, long long windows)
+{
+    dst[HB_C_NFEV] += k.nfev; dst[HB_C_NJEV] += k.njev; dst[HB_C_NLU] += k.nlu;
+    dst[HB_C_NSTEPS] += k.nsteps; dst[HB_C_NREJECT] += k.nreject; dst[HB_C_NFAIL] += k.nfail;
+    dst[HB_C_NRHS] += k.nrhs; dst[HB_C_NNEWTON] += k.nnewton; dst[HB_C_NWINDOWS] += windows;
+}
+
+// Closure on the nodes at the state in V_Y with the noise in V_NR (the
+// diagnostic call of simulation.py:564,623: node k uses n_rnd[k]).
+template <int NT>
+__device__ inline void nodes_diag(const DevCtx &c, int col, double *th, double *K, double *C, double *kb)
+{
+    const int nx = c.nx;
+    const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
+    for (int k = threadIdx.x; k < nx; k += NT) {
+        Clos r;
+        closure_cold(HB_X(c, X_PAR), HB_VEC(c, V_Y)[k], st[(size_t)HB_S_PHI_NODE * nx + k],
+                     st[(size_t)HB_S_KMEAN_NODE * nx + k], st[(size_t)HB_S_COEF_NODE * nx + k],
+                     HB_VEC(c, V_NR)[k], &r);
+        th[k] = r.theta; K[k] = r.K; kb[k] = r.kb;
+        if (C) C[k] = r.C;
+    }
+}
+
+// Diagnostics of one row: estimated water table, lateral flow of the last RHS
+// evaluation (arg_out, quirk Q6) and, on output rows, the closure on the nodes
+// (simulation.py:612-630).  State is in V_Y.
+template <int NT>
+__device__ inline void write_row(const DevCtx &c, int &parity, int col, int row, int status, bool solved)
+{
+    const int nx = c.nx, tid = threadIdx.x;
+    double *ws = c.wscal + ((size_t)col * c.T + row) * HB_NWSCAL;
+    if (status == 2) {
+        if (tid == 0) { ws[HB_W_WTD_EST] = 0.0; ws[HB_W_LATERAL] = 0.0; ws[HB_W_TRANSP] = 0.0; ws[HB_W_STATUS] = 2.0; }
+        return;
+    }
+    const int wtd_est = find_wtd_nodes<NT>(c, parity, HB_VEC(c, V_Y));
+    if (tid == 0) {
+        ws[HB_W_WTD_EST] = (double)wtd_est;
+        ws[HB_W_LATERAL] = solved ? lateral_flow<NT>(c) : 0.0;
+        ws[HB_W_TRANSP] = 0.0;
+        ws[HB_W_STATUS] = (double)status;
+    }
+    if (c.fields && c.out_stride > 0 && (row % c.out_stride == 0 || row == c.T - 1)) {
+        const int o = (row % c.out_stride == 0) ? row / c.out_stride : c.n_out - 1;
+        double *f = c.fields + ((size_t)col * c.n_out + o) * HB_NFIELD * nx;
+        for (int k = tid; k < nx; k += NT) f[(size_t)HB_F_PSI * nx + k] = HB_VEC(c, V_Y)[k];
+        nodes_diag<NT>(c, col, f + (size_t)HB_F_THETA * nx, f + (size_t)HB_F_K * nx, nullptr,
+                       f + (size_t)HB_F_KBKG * nx);
+    }
+}
+
+template <int NT, int CPT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
+{
+    __shared__ int s_col;
+    const int nx = c.nx, tid = threadIdx.x;
+    double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
+    int parity = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_col = atomicAdd(c.queue, 1);
+        __syncthreads();
+        const int col = s_col;
+        if (col >= c.n_cols) break;
+        bind_column<NT>(c, col);
+        double *psi_g = c.psi + (size_t)col * nx;
+        double *nb = c.noise_base + (size_t)col * nx;
+        for (int i = tid; i < nx; i += NT) { nr[i] = nb[i]; y[i] = psi_g[i]; }
+        bool nr_is_base = true;
+        const int ser = c.series ? c.series[col] : 0;
+        Counters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long windows = 0;
+        __syncthreads();
+        for (int row = w0; row < w1; ++row) {
+            int status = 0;
+            bool solved = false;
+            if (row > 0) {
+                const int wtd = c.wtd_idx[(size_t)ser * c.T + row];
+                if (wtd < 0) status = 2;
+                else {
+                    const double p = HB_X(c, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
+                    const bool refresh = (p > 0.5) || (row % 48 == 0);   // simulation.py:599
+                    __syncthreads();
+                    if (refresh) {
+                        if (c.noise_mode == HB_NOISE_TAPE) {
+                            const int slot = c.slot_next[col];          // uniform read
+                            const double *src = c.tape + ((size_t)col * c.n_slots + min(slot, c.n_slots - 1)) * nx;
+                            for (int i = tid; i < nx; i += NT) nr[i] = src[i];
+                            __syncthreads();
+                            if (tid == 0) c.slot_next[col] = slot + 1;
+                        } else {
+                            for (int i = tid; i < nx; i += NT)
+                                nr[i] = philox_normal(c.seed, c.col_offset + col, row, i);
+                        }
+                        nr_is_base = false;
+                    } else if (!nr_is_base) {
+                        for (int i = tid; i < nx; i += NT) nr[i] = nb[i];
+                        nr_is_base = true;
+                    }
+                    __syncthreads();
+                    Args a;
+                    a.precip = p; a.wtd = wtd;
+                    a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
+                    bool damped = false;
+                    status = solve_window<NT, CPT>(c, col, a, (double)(row - 1), (double)row, psi_g, cnt, damped);
+                    if (damped && nr_is_base)
+                        for (int i = tid; i < nx; i += NT) nb[i] = nr[i];
+                    for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
+                    windows++; solved = true;
+                }
+            }
+            write_row<NT>(c, parity, col, row, status, solved);
+        }
+        if (tid == 0) add_counters(c.counters + (size_t)col * HB_NCOUNTER, cnt, windows);
+    }
+}
+
+template <int NT, int CPT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) spinup_kernel(const __grid_constant__ DevCtx c, int max_iter,
+                                                                    const double *nrnd0, const double *zwtd0,
+                                                                    int *iters_out)
+{
+    __shared__ int s_col;
+    const int nx = c.nx, tid = threadIdx.x;
+    double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
+    int parity = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_col = atomicAdd(c.queue, 1);
+        __syncthreads();
+        const int col = s_col;
+        if (col >= c.n_cols) break;
+        bind_column<NT>(c, col);
+        double *psi_g = c.psi + (size_t)col * nx;
+        for (int i = tid; i < nx; i += NT)
+            nr[i] = nrnd0 ? nrnd0[(size_t)col * nx + i]
+                          : philox_normal(c.seed, c.col_offset + col, -1, i);
+        const int ser = c.series ? c.series[col] : 0;
+        __syncthreads();
+        Args a;
+        a.precip = HB_X(c, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T];
+        a.wtd = c.wtd_idx[(size_t)ser * c.T]; a.mode = 2;
+        const double dz = HB_X(c, X_PAR)[HB_P_DZ];
+        Counters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
+        int it = 0;
+        for (it = 0; it < max_iter; ++it) {
+            bool damped = false;
+            solve_window<NT, CPT>(c, col, a, 0.0, 1.0, psi_g, cnt, damped);
+            const int wtd_est = find_wtd_nodes<NT>(c, parity, y);
+            const double abs_err = fabs(zwtd0[col] - c.x[wtd_est]);
+            double loc = 0.0;
+            for (int i = tid; i < nx; i += NT) { const double dl = y[i] - psi_g[i]; loc += dl * dl; }
+            const double mse = block_sum<NT>(c, parity, loc) / (double)nx;
+            for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
+            if (abs_err <= 2.0 * dz && mse <= 0.01) { it++; break; }
+        }
+        if (tid == 0) {
+            add_counters(c.counters + (size_t)col * HB_NCOUNTER, cnt, it);
+            if (iters_out) iters_out[col] = it;
+        }
+    }
+}
+
+// ---- test hooks ---------------------------------------------------------------
+struct HookArgs {
+    int mode, col;
+    double precip, t0, t1, c;
+    int wtd, daylight, spinup, first;
+    double *io;          // device scratch: [8][nx]
+    long long *stats;    // [HB_NCOUNTER + 2]
+};
+enum { HK_RHS = 0, HK_NODES, HK_JAC, HK_TRI, HK_WINDOW };
+
+template <int NT, int CPT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) hook_kernel(const __grid_constant__ DevCtx c, HookArgs h)
+{
+    const int nx = c.nx, tid = threadIdx.x;
+    bind_column<NT>(c, h.col);
+    double *io = h.io;
+    double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR), *b = HB_VEC(c, V_B);
+    Args a;
+    a.precip = h.precip; a.wtd = h.wtd; a.mode = h.spinup ? 2 : (h.daylight ? 1 : 0);
+    Counters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < nx; i += NT) { y[i] = io[i]; nr[i] = io[nx + i]; }
+    __syncthreads();
+    if (h.mode == HK_RHS) {
+        rhs_eval<NT, CPT>(c, h.col, a.precip, a.wtd, a.mode, V_B);
+        for (int i = tid; i < nx; i += NT) io[2 * nx + i] = b[i];
+        __syncthreads();
+        if (tid == 0) io[3 * nx] = lateral_flow<NT>(c);
+    } else if (h.mode == HK_NODES) {
+        nodes_diag<NT>(c, h.col, io + 2 * nx, io + 3 * nx, io + 4 * nx, io + 5 * nx);
+    } else if (h.mode == HK_JAC) {
+        for (int i = tid; i < nx; i += NT) { b[i] = io[i]; if (!h.first) HB_VEC(c, V_FAC)[i] = io[2 * nx + i]; }
+        num_jac<NT, CPT>(c, h.col, a.precip, a.wtd, a.mode, V_B, h.first != 0, cnt);
+        for (int i = tid; i < nx; i += NT) {
+            io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
+            io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_VEC(c, V_FAC)[i];
+        }
+    } else if (h.mode == HK_TRI) {
+        for (int i = tid; i < nx; i += NT) {
+            HB_VEC(c, V_JL)[i] = io[2 * nx + i]; HB_VEC(c, V_JD)[i] = io[3 * nx + i];
+            HB_VEC(c, V_JU)[i] = io[4 * nx + i]; b[i] = io[5 * nx + i];
+        }
+        __syncthreads();
+        if (tid < 32) { tri_factor(c, h.c); tri_solve(c, h.c); }
+        __syncthreads();
+        for (int i = tid; i < nx; i += NT) io[6 * nx + i] = b[i];
+    } else if (h.mode == HK_WINDOW) {
+        bool damped = false;
+        const int st = solve_window<NT, CPT>(c, h.col, a, h.t0, h.t1, io, cnt, damped);
+        for (int i = tid; i < nx; i += NT) { io[2 * nx + i] = y[i]; io[nx + i] = nr[i]; }
+        __syncthreads();
+        if (tid == 0) {
+            io[3 * nx] = lateral_flow<NT>(c);
+            long long z[HB_NCOUNTER] = {0};
+            add_counters(z, cnt, 1);
+            for (int k = 0; k < HB_NCOUNTER; ++k) h.stats[k] = z[k];
+            h.stats[HB_NCOUNTER] = st;
+        }
+    }
+}
+
+__global__ void philox_base_kernel(DevCtx c)
+{
+    const size_t n = (size_t)c.n_cols * c.nx;
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n;
+         g += (size_t)gridDim.x * blockDim.x) {
+        const int col = (int)(g / c.nx), i = (int)(g % c.nx);
+        c.noise_base[g] = philox_normal(c.seed, c.col_offset + col, 0, i);
+    }
+}
+
+__global__ void moments_kernel(DevCtx c, double *sum, double *sumsq)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= c.T) return;
+    double s = 0.0, q = 0.0;
+    for (int col = 0; col < c.n_cols; ++col) {
+        const double *ws = c.wscal + ((size_t)col * c.T + row) * HB_NWSCAL;
+        if (ws[HB_W_STATUS] != 2.0) { const double v = ws[HB_W_WTD_EST]; s += v; q += v * v; }
+    }
+    sum[row] = s; sumsq[row] = q;
+}
+
+// ==================================================================================
+// Host side
+// ==================================================================================
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return -1; }
+#define CK(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess)                                                          \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct hb_ctx {
+    int device = 0;
+    DevCtx d{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::vector<void *> allocs;
+    double *hook_io = nullptr;
+    long long *hook_stats = nullptr;
+    int64_t launches = 0;
+    int sms = 0;
+    bool grid_set = false, cols_set = false, forcing_set = false;
+    int variant = 0;        // 0: <256,2>, 1: <512,2>, 2: <512,3>
+    size_t smem_bytes = 0;
+    int blocks_per_sm = 1;
+};
+
+template <typename T>
+static int dev_alloc(hb_ctx *ctx, T **p, size_t n)
+{
+    void *q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T) + 16));
+    CK(cudaMemset(q, 0, n * sizeof(T) + 16));
+    ctx->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return 0;
+}
+
+template <typename K>
+static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
+{
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nt, ctx->smem_bytes));
+    if (nb < 1) return fail("kernel does not fit on an SM");
+    ctx->blocks_per_sm = nb;
+    return 0;
+}
+
+#define DISPATCH(ctx, NAME, grid, ...)                                                     \
+    do {                                                                                   \
+        if ((ctx)->variant == 0)                                                           \
+            NAME<256, 2><<<grid, 256, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__);    \
+        else if ((ctx)->variant == 1)                                                      \
+            NAME<512, 2><<<grid, 512, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__);    \
+        else                                                                               \
+            NAME<512, 3><<<grid, 512, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->launches++;                                                                 \
+    } while (0)
+
+extern "C" {
+
+const char *hb_last_error(void) { return g_err.c_str(); }
+int hb_version(void) { return 100; }
+int hb_max_nx(void) { return 1320; }
+
+hb_ctx *hb_create(int device, int nx, int n_cols)
+{
+    if (nx < 4 || nx > hb_max_nx() || n_cols < 1) { fail("hb_create: bad nx / n_cols"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fail("hb_create: no CUDA device (this library has no CPU fallback)"); return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("hb_create: cudaSetDevice failed"); return nullptr; }
+    hb_ctx *ctx = new hb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sms = prop.multiProcessorCount;
+    DevCtx &d = ctx->d;
+    d.nx = nx; d.nxp = (nx + 1) & ~1; d.n_cols = n_cols;
+    d.rtol = 1e-3; d.atol = 1e-3;
+    ctx->variant = nx <= 512 ? 0 : (nx <= 1024 ? 1 : 2);
+    ctx->smem_bytes = smem_doubles(d.nxp) * sizeof(double);
+    {   // BDF coefficient tables exactly as scipy builds them (bdf.py:244-247)
+        const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
+        double gam[6], alp[6], erc[6];
+        gam[0] = 0.0;
+        for (int k = 1; k <= 5; ++k) gam[k] = gam[k - 1] + 1.0 / k;
+        for (int k = 0; k <= 5; ++k) { alp[k] = (1.0 - kappa[k]) * gam[k]; erc[k] = kappa[k] * gam[k] + 1.0 / (k + 1); }
+        if (cudaMemcpyToSymbol(hb::k_gamma, gam, sizeof(gam)) != cudaSuccess ||
+            cudaMemcpyToSymbol(hb::k_alpha, alp, sizeof(alp)) != cudaSuccess ||
+            cudaMemcpyToSymbol(hb::k_error_const, erc, sizeof(erc)) != cudaSuccess) {
+            fail("hb_create: constant upload failed"); delete ctx; return nullptr;
+        }
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail("hb_create: stream"); delete ctx; return nullptr;
+    }
+    ctx->stream = ctx->own_stream;
+    int rc = 0;
+    double *x, *dx, *zx, *xz, *par, *stat, *psi, *nb; int *grp, *queue, *slot; long long *cnt;
+    rc |= dev_alloc(ctx, &x, nx); rc |= dev_alloc(ctx, &dx, nx); rc |= dev_alloc(ctx, &zx, nx);
+    rc |= dev_alloc(ctx, &xz, nx); rc |= dev_alloc(ctx, &grp, nx);
+    rc |= dev_alloc(ctx, &par, (size_t)n_cols * HB_NPARAM);
+    rc |= dev_alloc(ctx, &stat, (size_t)n_cols * HB_NSTATIC * nx);
+    rc |= dev_alloc(ctx, &psi, (size_t)n_cols * nx);
+    rc |= dev_alloc(ctx, &nb, (size_t)n_cols * nx);
+    rc |= dev_alloc(ctx, &queue, 4); rc |= dev_alloc(ctx, &slot, n_cols);
+    rc |= dev_alloc(ctx, &cnt, (size_t)n_cols * HB_NCOUNTER);
+    rc |= dev_alloc(ctx, &ctx->hook_io, (size_t)8 * nx + 8);
+    rc |= dev_alloc(ctx, &ctx->hook_stats, HB_NCOUNTER + 2);
+    if (rc) { hb_destroy(ctx); return nullptr; }
+    d.x = x; d.dx = dx; d.zx = zx; d.xz = xz; d.grp = grp; d.par = par; d.stat = stat;
+    d.psi = psi; d.noise_base = nb; d.queue = queue; d.slot_next = slot; d.counters = cnt;
+    d.noise_mode = HB_NOISE_TAPE; d.n_slots = 0; d.tape = nullptr;
+#define PREP(NT_, CPT_)                                                        \
+    do {                                                                       \
+        rc = prep_kernel(ctx, hook_kernel<NT_, CPT_>, NT_);                    \
+        if (!rc) rc = prep_kernel(ctx, spinup_kernel<NT_, CPT_>, NT_);         \
+        if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_>, NT_);            \
+    } while (0)
+    if (ctx->variant == 0) PREP(256, 2);
+    else if (ctx->variant == 1) PREP(512, 2);
+    else PREP(512, 3);
+#undef PREP
+    if (rc) { hb_destroy(ctx); return nullptr; }
+    return ctx;
+}
+
+int hb_destroy(hb_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return 0;
+}
+
+int hb_set_stream(hb_ctx *ctx, void *s)
+{
+    if (!ctx) return fail("null ctx");
+    ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+    return 0;
+}
+
+int hb_sync(hb_ctx *ctx)
+{
+    if (!ctx) return fail("null ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_set_grid(hb_ctx *ctx, const double *x, const int32_t *groups, int n_groups)
+{
+    if (!ctx || !x || !groups) return fail("hb_set_grid: null argument");
+    const int nx = ctx->d.nx;
+    std::vector<double> dx(nx, 1.0), zx(nx, 0.0), xz(nx, 0.0), xm(nx, 0.0);
+    for (int k = 0; k + 1 < nx; ++k) {
+        dx[k] = x[k + 1] - x[k];
+        if (!(dx[k] > 0.0)) return fail("hb_set_grid: Space domain is not increasing.");
+        xm[k] = x[k] + 0.5 * dx[k];            // richards_pde.py:67
+        zx[k] = xm[k] - x[k];                  // richards_pde.py:79
+    }
+    for (int k = 1; k < nx; ++k) xz[k] = x[k] - xm[k - 1];   // richards_pde.py:76
+    if (n_groups < 1 || n_groups > 8) return fail("hb_set_grid: n_groups out of range");
+    for (int k = 0; k < nx; ++k) {
+        if (groups[k] < 0 || groups[k] >= n_groups) return fail("hb_set_grid: bad group id");
+        if (k > 0 && groups[k] == groups[k - 1]) return fail("hb_set_grid: colouring is not valid");
+        if (k > 1 && groups[k] == groups[k - 2]) return fail("hb_set_grid: colouring is not valid");
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync((void *)ctx->d.x, x, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void *)ctx->d.dx, dx.data(), nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void *)ctx->d.zx, zx.data(), nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void *)ctx->d.xz, xz.data(), nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void *)ctx->d.grp, groups, nx * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->d.ng = n_groups;
+    ctx->grid_set = true;
+    return 0;
+}
+
+int hb_set_tolerances(hb_ctx *ctx, double rtol, double atol)
+{
+    if (!ctx || !(rtol > 0.0) || !(atol >= 0.0)) return fail("hb_set_tolerances: bad argument");
+    ctx->d.rtol = rtol; ctx->d.atol = atol;
+    return 0;
+}
+
+static int range_ok(hb_ctx *ctx, int col0, int ncol)
+{
+    if (!ctx) return fail("null ctx");
+    if (col0 < 0 || ncol < 0 || col0 + ncol > ctx->d.n_cols) return fail("column range out of bounds");
+    return 0;
+}
+
+int hb_set_columns(hb_ctx *ctx, int col0, int ncol, const double *par, const double *stat)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    if (!par || !stat) return fail("hb_set_columns: null argument");
+    const int nx = ctx->d.nx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync((void *)(ctx->d.par + (size_t)col0 * HB_NPARAM), par,
+                       (size_t)ncol * HB_NPARAM * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void *)(ctx->d.stat + (size_t)col0 * HB_NSTATIC * nx), stat,
+                       (size_t)ncol * HB_NSTATIC * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->cols_set = true;
+    return 0;
+}
+
+int hb_set_state(hb_ctx *ctx, int col0, int ncol, const double *psi)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d.psi + (size_t)col0 * ctx->d.nx, psi, (size_t)ncol * ctx->d.nx * sizeof(double),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int hb_get_state(hb_ctx *ctx, int col0, int ncol, double *psi)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(psi, ctx->d.psi + (size_t)col0 * ctx->d.nx, (size_t)ncol * ctx->d.nx * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_set_forcing(hb_ctx *ctx, int n_series, int T, const double *precip, const int32_t *wtd_idx,
+                   const int32_t *daylight, const double *atm, const int32_t *series_of_col)
+{
+    if (!ctx || !precip || !wtd_idx || !daylight) return fail("hb_set_forcing: null argument");
+    if (n_series < 1 || T < 1) return fail("hb_set_forcing: empty forcing");
+    DevCtx &d = ctx->d;
+    const size_t n = (size_t)n_series * T;
+    for (size_t k = 0; k < n; ++k)
+        if (wtd_idx[k] >= d.nx) return fail("hb_set_forcing: water-table index outside the grid");
+    if (series_of_col)
+        for (int k = 0; k < d.n_cols; ++k)
+            if (series_of_col[k] < 0 || series_of_col[k] >= n_series) return fail("hb_set_forcing: bad series id");
+    CK(cudaSetDevice(ctx->device));
+    double *p, *a; int *w, *dl, *s = nullptr;
+    if (dev_alloc(ctx, &p, n) || dev_alloc(ctx, &a, n) || dev_alloc(ctx, &w, n) || dev_alloc(ctx, &dl, n)) return -1;
+    CK(cudaMemcpyAsync(p, precip, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (atm) CK(cudaMemcpyAsync(a, atm, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(w, wtd_idx, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dl, daylight, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (series_of_col) {
+        if (dev_alloc(ctx, &s, d.n_cols)) return -1;
+        CK(cudaMemcpyAsync(s, series_of_col, d.n_cols * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    d.precip = p; d.atm = a; d.wtd_idx = w; d.daylight = dl; d.series = s;
+    d.n_series = n_series; d.T = T;
+    double *ws;
+    if (dev_alloc(ctx, &ws, (size_t)d.n_cols * T * HB_NWSCAL)) return -1;
+    d.wscal = ws; d.fields = nullptr; d.n_out = 0; d.out_stride = 0;
+    ctx->forcing_set = true;
+    return 0;
+}
+
+int hb_set_noise_tape(hb_ctx *ctx, int col0, int ncol, int n_slots, const double *tape)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    if (n_slots < 1 || !tape) return fail("hb_set_noise_tape: bad argument");
+    DevCtx &d = ctx->d;
+    CK(cudaSetDevice(ctx->device));
+    if (d.n_slots != n_slots || !d.tape) {
+        double *t;
+        if (dev_alloc(ctx, &t, (size_t)d.n_cols * n_slots * d.nx)) return -1;
+        d.tape = t; d.n_slots = n_slots;
+    }
+    CK(cudaMemcpyAsync((void *)(d.tape + (size_t)col0 * n_slots * d.nx), tape,
+                       (size_t)ncol * n_slots * d.nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // slot 0 is the run's first draw: it becomes the (mutable) base field
+    CK(cudaMemcpy2DAsync(d.noise_base + (size_t)col0 * d.nx, d.nx * sizeof(double),
+                         d.tape + (size_t)col0 * n_slots * d.nx, (size_t)n_slots * d.nx * sizeof(double),
+                         d.nx * sizeof(double), ncol, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<int> ones(ncol, 1);
+    CK(cudaMemcpyAsync(d.slot_next + col0, ones.data(), ncol * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    d.noise_mode = HB_NOISE_TAPE;
+    return 0;
+}
+
+int hb_set_noise_philox(hb_ctx *ctx, uint64_t seed, int64_t first_global_column)
+{
+    if (!ctx) return fail("null ctx");
+    DevCtx &d = ctx->d;
+    d.noise_mode = HB_NOISE_PHILOX; d.seed = seed; d.col_offset = first_global_column;
+    CK(cudaSetDevice(ctx->device));
+    philox_base_kernel<<<ctx->sms * 4, 256, 0, ctx->stream>>>(d);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_set_output(hb_ctx *ctx, int out_stride)
+{
+    if (!ctx || !ctx->forcing_set) return fail("hb_set_output: call hb_set_forcing first");
+    DevCtx &d = ctx->d;
+    if (out_stride <= 0) { d.out_stride = 0; d.n_out = 0; d.fields = nullptr; return 0; }
+    d.out_stride = out_stride;
+    d.n_out = (d.T - 1) / out_stride + 1 + (((d.T - 1) % out_stride) != 0);
+    double *f;
+    CK(cudaSetDevice(ctx->device));
+    if (dev_alloc(ctx, &f, (size_t)d.n_cols * d.n_out * HB_NFIELD * d.nx)) return -1;
+    d.fields = f;
+    return 0;
+}
+
+int hb_n_output_rows(hb_ctx *ctx) { return ctx ? ctx->d.n_out : -1; }
+
+static int ready(hb_ctx *ctx)
+{
+    if (!ctx) return fail("null ctx");
+    if (!ctx->grid_set) return fail("grid not set (hb_set_grid)");
+    if (!ctx->cols_set) return fail("columns not set (hb_set_columns)");
+    return 0;
+}
+
+static int persistent_grid(hb_ctx *ctx)
+{
+    const int cap = ctx->sms * ctx->blocks_per_sm;
+    return ctx->d.n_cols < cap ? ctx->d.n_cols : cap;
+}
+
+int hb_spinup(hb_ctx *ctx, int max_iter, const double *nrnd0, const double *zwtd0_cm, int32_t *iters_out)
+{
+    if (ready(ctx)) return -1;
+    if (!ctx->forcing_set) return fail("hb_spinup: forcing not set");
+    if (!zwtd0_cm) return fail("hb_spinup: null zwtd0_cm");
+    DevCtx &d = ctx->d;
+    if (d.noise_mode == HB_NOISE_TAPE && !nrnd0) return fail("hb_spinup: TAPE mode needs nrnd0");
+    CK(cudaSetDevice(ctx->device));
+    double *nr = nullptr, *zw; int *it;
+    if (nrnd0) {
+        if (dev_alloc(ctx, &nr, (size_t)d.n_cols * d.nx)) return -1;
+        CK(cudaMemcpyAsync(nr, nrnd0, (size_t)d.n_cols * d.nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (dev_alloc(ctx, &zw, d.n_cols) || dev_alloc(ctx, &it, d.n_cols)) return -1;
+    CK(cudaMemcpyAsync(zw, zwtd0_cm, d.n_cols * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d.queue, 0, sizeof(int), ctx->stream));
+    const int grid = persistent_grid(ctx);
+    DISPATCH(ctx, spinup_kernel, grid, d, max_iter, nr, zw, it);
+    CK(cudaGetLastError());
+    if (iters_out) {
+        CK(cudaMemcpyAsync(iters_out, it, d.n_cols * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int hb_run(hb_ctx *ctx, int w0, int w1)
+{
+    if (ready(ctx)) return -1;
+    if (!ctx->forcing_set) return fail("hb_run: forcing not set");
+    DevCtx &d = ctx->d;
+    if (w0 < 0 || w1 > d.T || w0 >= w1) return fail("hb_run: bad window range");
+    if (d.noise_mode == HB_NOISE_TAPE && !d.tape) return fail("hb_run: noise not set");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(d.queue, 0, sizeof(int), ctx->stream));
+    const int grid = persistent_grid(ctx);
+    DISPATCH(ctx, run_kernel, grid, d, w0, w1);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_get_wscal(hb_ctx *ctx, int col0, int ncol, double *wscal)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    if (!ctx->forcing_set) return fail("hb_get_wscal: forcing not set");
+    const size_t per = (size_t)ctx->d.T * HB_NWSCAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(wscal, ctx->d.wscal + col0 * per, ncol * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_get_fields(hb_ctx *ctx, int col0, int ncol, double *fields)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    if (!ctx->d.fields) return fail("hb_get_fields: no field output planned (hb_set_output)");
+    const size_t per = (size_t)ctx->d.n_out * HB_NFIELD * ctx->d.nx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(fields, ctx->d.fields + col0 * per, ncol * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_get_counters(hb_ctx *ctx, int col0, int ncol, int64_t *counters)
+{
+    if (range_ok(ctx, col0, ncol)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(counters, ctx->d.counters + (size_t)col0 * HB_NCOUNTER,
+                       (size_t)ncol * HB_NCOUNTER * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int hb_reset_counters(hb_ctx *ctx)
+{
+    if (!ctx) return fail("null ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d.counters, 0, (size_t)ctx->d.n_cols * HB_NCOUNTER * sizeof(long long), ctx->stream));
+    return 0;
+}
+
+int hb_wtd_moments_dev(hb_ctx *ctx, double *sum_dev, double *sumsq_dev)
+{
+    if (!ctx || !ctx->forcing_set) return fail("hb_wtd_moments_dev: forcing not set");
+    CK(cudaSetDevice(ctx->device));
+    moments_kernel<<<(ctx->d.T + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, sum_dev, sumsq_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int64_t hb_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+// ---- hooks -----------------------------------------------------------------------
+static int run_hook(hb_ctx *ctx, HookArgs h)
+{
+    h.io = ctx->hook_io; h.stats = ctx->hook_stats;
+    DISPATCH(ctx, hook_kernel, 1, ctx->d, h);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int hook_in(hb_ctx *ctx, int slot, const double *src)
+{
+    CK(cudaMemcpyAsync(ctx->hook_io + (size_t)slot * ctx->d.nx, src, ctx->d.nx * sizeof(double),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+static int hook_out(hb_ctx *ctx, int slot, double *dst, int n)
+{
+    CK(cudaMemcpyAsync(dst, ctx->hook_io + (size_t)slot * ctx->d.nx, n * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int hb_rhs(hb_ctx *ctx, int col, const double *psi, const double *nrnd, double precip, int wtd,
+           int daylight, int spinup, double *dydt, double *lateral_flow)
+{
+    if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (hook_in(ctx, 0, psi) || hook_in(ctx, 1, nrnd)) return -1;
+    HookArgs h{}; h.mode = HK_RHS; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight; h.spinup = spinup;
+    if (run_hook(ctx, h)) return -1;
+    if (hook_out(ctx, 2, dydt, ctx->d.nx)) return -1;
+    if (lateral_flow && hook_out(ctx, 3, lateral_flow, 1)) return -1;
+    return 0;
+}
+
+int hb_closure_nodes(hb_ctx *ctx, int col, const double *psi, const double *nrnd, double *out)
+{
+    if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (hook_in(ctx, 0, psi) || hook_in(ctx, 1, nrnd)) return -1;
+    HookArgs h{}; h.mode = HK_NODES; h.col = col;
+    if (run_hook(ctx, h)) return -1;
+    return hook_out(ctx, 2, out, 4 * ctx->d.nx);
+}
+
+int hb_num_jac(hb_ctx *ctx, int col, const double *psi, const double *nrnd, double precip, int wtd,
+               int daylight, int spinup, const double *fac_in, double *dl, double *d, double *du,
+               double *fac_out)
+{
+    if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (hook_in(ctx, 0, psi) || hook_in(ctx, 1, nrnd)) return -1;
+    if (fac_in && hook_in(ctx, 2, fac_in)) return -1;
+    HookArgs h{}; h.mode = HK_JAC; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight;
+    h.spinup = spinup; h.first = fac_in ? 0 : 1;
+    if (run_hook(ctx, h)) return -1;
+    if (hook_out(ctx, 3, dl, ctx->d.nx) || hook_out(ctx, 4, d, ctx->d.nx) ||
+        hook_out(ctx, 5, du, ctx->d.nx) || hook_out(ctx, 6, fac_out, ctx->d.nx)) return -1;
+    return 0;
+}
+
+int hb_tri_solve(hb_ctx *ctx, const double *dl, const double *d, const double *du, double c,
+                 const double *b, double *x)
+{
+    if (ready(ctx)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> zero(ctx->d.nx, 0.0);
+    if (hook_in(ctx, 0, zero.data()) || hook_in(ctx, 1, zero.data()) || hook_in(ctx, 2, dl) ||
+        hook_in(ctx, 3, d) || hook_in(ctx, 4, du) || hook_in(ctx, 5, b)) return -1;
+    HookArgs h{}; h.mode = HK_TRI; h.col = 0; h.c = c;
+    if (run_hook(ctx, h)) return -1;
+    return hook_out(ctx, 6, x, ctx->d.nx);
+}
+
+int hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0, double *nrnd,
+                    double precip, int wtd, int daylight, int spinup, double *y_end,
+                    int64_t *stats, double *lateral_flow, int *status)
+{
+    if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
+    CK(cudaSetDevice(ctx->device));
+    if (hook_in(ctx, 0, y0) || hook_in(ctx, 1, nrnd)) return -1;
+    HookArgs h{}; h.mode = HK_WINDOW; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight;
+    h.spinup = spinup; h.t0 = t0; h.t1 = t1;
+    if (run_hook(ctx, h)) return -1;
+    if (hook_out(ctx, 2, y_end, ctx->d.nx) || hook_out(ctx, 1, nrnd, ctx->d.nx)) return -1;
+    if (lateral_flow && hook_out(ctx, 3, lateral_flow, 1)) return -1;
+    long long st[HB_NCOUNTER + 2];
+    CK(cudaMemcpy(st, ctx->hook_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    if (stats) for (int k = 0; k < HB_NCOUNTER; ++k) stats[k] = st[k];
+    if (status) *status = (int)st[HB_NCOUNTER];
+    return 0;
+}
+
+}  // extern "C"

@@ -32,8 +32,11 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        build()
-        _lib = ct.CDLL(_LIB_PATH)
+        path = os.environ.get("HB_ORACLE_LIB")     # experiments only
+        if not path:
+            build()
+            path = _LIB_PATH
+        _lib = ct.CDLL(path)
         _lib.orc_solve_window_c.restype = ct.c_int
         _lib.orc_run_c.restype = ct.c_int
         _lib.orc_spinup_c.restype = ct.c_int

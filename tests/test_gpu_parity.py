@@ -1,0 +1,242 @@
+"""
+GPU parity tests (run on the B200 box): every piece of the CUDA path, called
+through the C-ABI, against the CPU oracle on the same inputs and against the
+golden outputs of the unmodified reference.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from hydromodel_b200 import capi, pack
+from helpers import (column_from_json, default_column, rhs_cases, rhs_configs, tol_scaled)
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ctx(col, n_cols=1):
+    nx = col["x"].size
+    ctx = capi.Context(nx, n_cols)
+    grp, ng = pack.fd_groups(nx)
+    ctx.set_grid(col["x"], grp, ng)
+    ctx.set_columns(np.tile(col["par"], (n_cols, 1)), np.tile(col["stat"], (n_cols, 1, 1)))
+    return ctx, grp
+
+
+def test_rhs_and_closure_against_reference_and_oracle(golden):
+    """K1: RichardsPDE.__call__ on the device.  |d(dpsi/dt)| <= 1e-12 * (sum of
+    the magnitudes of the terms that cancel in each component); closure outputs
+    theta, K, C, K_bkg 1e-12 relative."""
+    g = golden("rhs_cases.npz")
+    n_cases = 0
+    for cfg in rhs_configs(g):
+        col = column_from_json(g[f"{cfg}/params_json"])
+        ctx, _ = make_ctx(col)
+        for _, psi, nr, precip, wtd, spin, p in rhs_cases(g, cfg):
+            dydt, lat = ctx.rhs(0, psi, nr, precip, wtd, 0, spin)
+            o_dydt, o_lat, cond = oracle.rhs(col["x"], col["par"], col["stat"], psi, nr, precip,
+                                             wtd, 0, spin, with_cond=True)
+            assert np.all(np.abs(dydt - o_dydt) <= 1e-12 * cond + 1e-300), (cfg, p)
+            assert np.all(np.abs(dydt - g[p + "dydt"]) <= 1e-12 * cond + 1e-300), (cfg, p)
+            assert lat == pytest.approx(float(g[p + "lat"]), rel=1e-12, abs=1e-300)
+            nodes = ctx.closure_nodes(0, psi, nr)
+            assert np.allclose(nodes, g[p + "nodes"], rtol=1e-12, atol=0), (cfg, p)
+            n_cases += 1
+        ctx.close()
+    assert n_cases >= 250
+
+
+def test_tridiagonal_partition_solver():
+    """K3: (I - cJ) x = b with the warp partition/PCR solver vs a dense solve,
+    for several sizes incl. ragged chunking (nx not a multiple of 32)."""
+    rng = np.random.default_rng(0)
+    for nx in (401, 101, 37, 512, 1001):
+        x = np.arange(nx) * 5.0
+        ctx = capi.Context(nx, 1)
+        grp, ng = pack.fd_groups(nx)
+        ctx.set_grid(x, grp, ng)
+        ctx.set_columns(np.zeros((1, pack.NPARAM)), np.zeros((1, pack.NSTATIC, nx)))
+        for c in (1e-3, 0.3):
+            d = -rng.uniform(1.0, 500.0, nx)
+            dl = np.r_[0.0, rng.uniform(0.1, 200.0, nx - 1)]
+            du = np.r_[rng.uniform(0.1, 200.0, nx - 1), 0.0]
+            b = rng.standard_normal(nx)
+            A = np.eye(nx) - c * (np.diag(d) + np.diag(dl[1:], -1) + np.diag(du[:-1], 1))
+            ref = np.linalg.solve(A, b)
+            got = ctx.tri_solve(dl, d, du, c, b)
+            assert np.allclose(got, ref, rtol=1e-10, atol=1e-13 * np.abs(ref).max()), (nx, c)
+        ctx.close()
+
+
+def test_num_jac_against_scipy_and_oracle(golden):
+    """K2: grouped forward-difference Jacobian; same zero pattern and step
+    factors as scipy's num_jac, entries within 1e-5 relative."""
+    g = golden("jac_cases.npz")
+    col = default_column()
+    ctx, grp = make_ctx(col)
+    for name in ("spun", "rain"):
+        psi, nr, precip = g[name + "/psi"], g[name + "/n_rnd"], float(g[name + "/precip"])
+        dl, d, du, fac = ctx.num_jac(0, psi, nr, precip, 170)
+        for mine, ref in ((dl, np.r_[0, g[name + "/dl"]]), (d, g[name + "/d"]),
+                          (du, np.r_[g[name + "/du"], 0])):
+            assert np.array_equal(mine == 0, ref == 0)
+            assert np.allclose(mine, ref, rtol=1e-5, atol=0)
+        assert np.array_equal(fac, g[name + "/factor"])
+        _, d2, _, fac2 = ctx.num_jac(0, psi, nr, precip, 170, fac=fac)
+        assert np.array_equal(fac2, g[name + "/factor_second"])
+    ctx.close()
+
+
+def _teacher_forced_gpu(g, prefix, col, spinup, limit=None):
+    ctx, grp = make_ctx(col)
+    n = g[prefix + "y0"].shape[0] if limit is None else min(limit, g[prefix + "y0"].shape[0])
+    errs, same, wtd_ok, o_errs = [], [], [], []
+    psi_sat = col["par"][pack.P_PSI_SAT]
+    for w in range(n):
+        nr = g[prefix + "n_rnd"][w].copy()
+        t0 = float(g[prefix + "t0"][w])
+        y, st, status, lat = ctx.solve_window(0, t0, t0 + 1.0, g[prefix + "y0"][w], nr,
+                                              float(g[prefix + "precip"][w]),
+                                              int(g[prefix + "wtd"][w]), 0, spinup)
+        ref = g[prefix + "y_end"][w]
+        assert status == 0
+        errs.append(tol_scaled(y, ref))
+        same.append(st["nfev"] == g[prefix + "nfev"][w] and st["njev"] == g[prefix + "njev"][w]
+                    and st["nlu"] == g[prefix + "nlu"][w] and st["nsteps"] == g[prefix + "nsteps"][w])
+        wtd_ok.append(oracle.find_wtd(y >= psi_sat) == oracle.find_wtd(ref >= psi_sat))
+    ctx.close()
+    return np.array(errs), np.array(same), np.array(wtd_ok)
+
+
+def test_windows_default_run_against_reference(golden):
+    """K4+K5 teacher-forced: same bar as the oracle's own test
+    (tests/test_oracle.py::test_windows_default_run_against_reference)."""
+    g = golden("windows_default.npz")
+    errs, same, wtd_ok = _teacher_forced_gpu(g, "", default_column(), 0)
+    print("gpu windows: counters-match %.3f  err median %.2e  p95 %.2e  max %.2e" %
+          (same.mean(), np.median(errs), np.quantile(errs, 0.95), errs.max()))
+    assert same.mean() >= 0.95
+    assert np.mean(errs <= 0.1) >= 0.95 and errs.max() < 5.0
+    assert np.median(errs) < 1e-4
+    assert wtd_ok.all()
+
+
+def test_windows_spinup_against_reference(golden):
+    g = golden("spinup_default.npz")
+    errs, same, wtd_ok = _teacher_forced_gpu(g, "", default_column(), 1)
+    print("gpu spinup windows: counters-match %.3f  err median %.2e max %.2e" %
+          (same.mean(), np.median(errs), errs.max()))
+    assert same.mean() >= 0.75
+    assert np.median(errs) < 1e-2
+    assert wtd_ok.mean() >= 0.9
+
+
+@pytest.mark.parametrize("name", ["vg_strat", "vf_constant", "vf_linear", "vf_exponential",
+                                  "ens0", "ens1", "ens2", "mix3", "mix4", "mix5", "mix6", "lam2"])
+def test_windows_variants_against_reference(golden, name):
+    g = golden("windows_variants.npz")
+    col = column_from_json(g[f"{name}/params_json"])
+    errs, same, wtd_ok = _teacher_forced_gpu(g, name + "/", col, 0)
+    assert same.mean() >= 0.9
+    assert np.mean(errs <= 0.2) >= 0.9 and errs.max() < 5.0
+    assert wtd_ok.all()
+
+
+def test_windows_fine_grid_against_reference(golden):
+    """nx = 1001 (config 5): the 512-thread kernel variant."""
+    import os
+    import tempfile
+    from hydromodel_b200.synthetic import default_params, synthetic_forcing, fine_grid_site
+    g = golden("windows_fine.npz")
+    site = fine_grid_site(os.path.join(tempfile.mkdtemp(), "site.json"))
+    col = pack.pack_column(default_params(site), synthetic_forcing(365, stiff=True))
+    errs, same, wtd_ok = _teacher_forced_gpu(g, "", col, 0)
+    assert same.mean() >= 0.6
+    assert np.mean(errs <= 0.5) >= 0.8
+
+
+def _golden_tape(g, f, T):
+    base, slots = None, []
+    for i in range(1, T):
+        if f["precipitation_cm"][i] > 0.5 or i % 48 == 0:
+            slots.append(g["n_rnd"][i - 1])
+        elif base is None:
+            base = g["n_rnd"][i - 1]
+    return np.stack([base] + slots)
+
+
+def test_free_running_ensemble_against_reference_and_oracle(golden):
+    """hb_run on an ensemble of identical columns (host noise tape): every
+    column must reproduce the oracle's free-running loop, and the reference's
+    recorded run, over 60 windows: water-table node identical, psi within one
+    tolerance unit, theta 1e-4 relative at the output rows."""
+    g = golden("windows_default.npz")
+    col = default_column()
+    f = col["forcing"]
+    T, C = 61, 8
+    tape = _golden_tape(g, f, T)
+    ctx, grp = make_ctx(col, n_cols=C)
+    ctx.set_forcing(f["precipitation_cm"][:T], f["wtd_idx"][:T], f["daylight"][:T], f["atm"][:T])
+    ctx.set_output(10)
+    ctx.set_noise_tape(np.tile(tape[None], (C, 1, 1)))
+    ctx.set_state(np.tile(g["ic"], (C, 1)))
+    ctx.run(0, T)
+    psi = ctx.get_state()
+    wscal = ctx.get_wscal()
+    fields = ctx.get_fields()
+    counters = ctx.get_counters()
+    o_psi, o_wscal, o_fields, o_stats, used = oracle.run(
+        col["x"], grp, col["par"], col["stat"], f["precipitation_cm"][:T], f["wtd_idx"][:T],
+        f["daylight"][:T], f["atm"][:T], tape, g["ic"], out_stride=10)
+    for c in range(C):
+        assert np.array_equal(psi[c], psi[0])                 # columns are deterministic
+        assert np.array_equal(wscal[c], wscal[0])
+    assert np.array_equal(wscal[0, :, pack.W_WTD_EST] * 5.0, g["wtd_est_cm"][:T])
+    assert np.array_equal(wscal[0, :, pack.W_WTD_EST], o_wscal[:, pack.W_WTD_EST])
+    assert tol_scaled(psi[0], g["psi_press"][T - 1]) < 1.0
+    assert tol_scaled(psi[0], o_psi) < 1.0
+    assert fields.shape == (C, 7, 4, 401)
+    for o, row in enumerate(range(0, T, 10)):
+        assert np.allclose(fields[0, o, pack.F_THETA], g["theta_vol"][row], rtol=1e-4)
+        assert np.allclose(fields[0, o, pack.F_KBKG], g["K_bkg"][row], rtol=1e-4)
+    assert np.allclose(wscal[0, 1:, pack.W_LATERAL], g["out_lateral_flow"][:T - 1], rtol=1e-3, atol=1e-9)
+    assert counters[0, pack.C_NWINDOWS] == T - 1
+    assert abs(counters[0, pack.C_NFEV] - o_stats[pack.C_NFEV]) <= 0.05 * o_stats[pack.C_NFEV]
+    ctx.close()
+
+
+def test_spinup_kernel_against_oracle(golden):
+    """hb_spinup vs the oracle's spin-up loop, capped at 4 iterations (the
+    saturated start is the stiffest regime; later iterations drift apart by
+    decision flips, which the window-level tests quantify)."""
+    g = golden("spinup_default.npz")
+    col = default_column()
+    f = col["forcing"]
+    ctx, grp = make_ctx(col, n_cols=2)
+    psi0 = pack.saturated_initial_state(col["objs"])
+    nr = g["n_rnd"][0]
+    ctx.set_forcing(f["precipitation_cm"], f["wtd_idx"], f["daylight"], f["atm"])
+    ctx.set_state(np.tile(psi0, (2, 1)))
+    iters = ctx.spinup(f["zWtd_cm"][0], np.tile(nr, (2, 1)), max_iter=4)
+    psi = ctx.get_state()
+    o_psi, o_it, o_stats, _ = oracle.spinup(col["x"], grp, col["par"], col["stat"],
+                                            f["precipitation_cm"][0], f["wtd_idx"][0],
+                                            f["zWtd_cm"][0], nr, psi0, max_iter=4)
+    assert list(iters) == [o_it, o_it]
+    assert np.array_equal(psi[0], psi[1])
+    assert np.array_equal(psi0, g["y0"][0])
+    assert tol_scaled(psi[0], o_psi) < 5.0
+    psi_sat = col["par"][pack.P_PSI_SAT]
+    assert abs(oracle.find_wtd(psi[0] >= psi_sat) - oracle.find_wtd(o_psi >= psi_sat)) <= 1
+    ctx.close()
+
+
+def test_error_paths():
+    col = default_column()
+    ctx, grp = make_ctx(col)
+    with pytest.raises(capi.HydroB200Error):
+        ctx.run(0, 10)                       # forcing not set
+    with pytest.raises(capi.HydroB200Error):
+        ctx.set_grid(col["x"][::-1].copy(), grp)     # decreasing grid
+    with pytest.raises(capi.HydroB200Error):
+        capi.Context(5000, 1)                # nx beyond the shared-memory design
+    ctx.close()

@@ -1,0 +1,195 @@
+"""
+CPU tests: the oracle (oracle/hb_oracle.c) against the golden outputs of the
+unmodified reference (tests/golden/*.npz, made by tests/golden/make_golden.py)
+and against the reference's own known-answer vectors.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from hydromodel_b200 import pack
+from helpers import (column_from_json, default_column, rhs_cases, rhs_configs, tol_scaled)
+
+
+def test_find_wtd_reference_vectors():
+    """The four exact vectors of the reference's own test
+    (code/tests/test_utilities.py:56-86): expected 9, 0, 6, 7."""
+    a = np.ones(10, dtype=bool); a[:9] = False          # dry above the last cell
+    assert oracle.find_wtd(np.r_[np.zeros(9, bool), True]) == 9
+    assert oracle.find_wtd(np.ones(10, bool)) == 0
+    v = np.array([0, 0, 1, 0, 1, 0, 1, 1, 1, 1], dtype=bool)
+    assert oracle.find_wtd(v) == 6
+    v = np.array([1, 1, 1, 0, 1, 1, 0, 1, 1, 1], dtype=bool)
+    assert oracle.find_wtd(v) == 7
+    from hydromodel_b200.src.utilities import find_wtd
+    for vec in (np.r_[np.zeros(9, bool), True], np.ones(10, bool), v):
+        assert find_wtd(vec) == oracle.find_wtd(vec)
+
+
+def test_fd_colouring_matches_scipy(golden):
+    g = golden("jac_cases.npz")
+    grp, ng = pack.fd_groups(401)
+    assert ng == 5 and np.array_equal(grp, g["groups"])
+
+
+def test_fd_colouring_1001(golden):
+    import os
+    from conftest import GOLDEN
+    grp, ng = pack.fd_groups(1001)
+    assert ng == 5 and np.array_equal(grp, np.load(os.path.join(GOLDEN, "groups_1001.npy")))
+
+
+def test_static_pack_matches_reference_profiles(golden):
+    g = golden("rhs_cases.npz")
+    for cfg in rhs_configs(g):
+        col = column_from_json(g[f"{cfg}/params_json"])
+        assert np.array_equal(col["x"], g[f"{cfg}/z"])
+        assert np.array_equal(col["objs"]["porosity"].profile, g[f"{cfg}/porosity"])
+        assert np.array_equal(col["forcing"]["zWtd_cm"], g[f"{cfg}/zwtd_cm"])
+        assert np.array_equal(col["forcing"]["atm"], g[f"{cfg}/atm_series"])
+        assert col["forcing"]["surface_evap"] == float(g[f"{cfg}/surface_evap"])
+
+
+def test_rhs_against_reference(golden):
+    """RichardsPDE.__call__ parity.  Tolerance: 1e-12 of the magnitude sum of
+    the terms whose (cancelling) sum forms dpsi/dt; closure outputs 1e-12
+    relative (measured: 6e-14 and 5e-14)."""
+    g = golden("rhs_cases.npz")
+    n_cases = 0
+    for cfg in rhs_configs(g):
+        col = column_from_json(g[f"{cfg}/params_json"])
+        for _, psi, nr, precip, wtd, spin, p in rhs_cases(g, cfg):
+            dydt, lat, cond = oracle.rhs(col["x"], col["par"], col["stat"], psi, nr, precip,
+                                         wtd, 0, spin, with_cond=True)
+            ref = g[p + "dydt"]
+            assert np.all(np.abs(dydt - ref) <= 1e-12 * cond + 1e-300), (cfg, p)
+            nodes, qinf = oracle.closure_nodes(col["x"], col["par"], col["stat"], psi, nr)
+            assert np.allclose(nodes, g[p + "nodes"], rtol=1e-12, atol=0), (cfg, p)
+            assert qinf == pytest.approx(float(g[p + "qinf"]), rel=1e-12)
+            assert lat == pytest.approx(float(g[p + "lat"]), rel=1e-12, abs=1e-300)
+            n_cases += 1
+    assert n_cases >= 250
+
+
+def test_num_jac_against_scipy(golden):
+    """Tridiagonal FD Jacobian: entries within 1e-5 relative (forward
+    differences amplify 1e-16 differences of f by 1/h ~ 1e8), zero pattern and
+    step factors identical."""
+    g = golden("jac_cases.npz")
+    col = default_column()
+    grp, _ = pack.fd_groups(401)
+    for name in ("spun", "rain"):
+        psi, nr, precip = g[name + "/psi"], g[name + "/n_rnd"], float(g[name + "/precip"])
+        dl, d, du, fac = oracle.num_jac(col["x"], grp, col["par"], col["stat"], psi, nr, precip, 170)
+        for mine, ref in ((dl, np.r_[0, g[name + "/dl"]]), (d, g[name + "/d"]),
+                          (du, np.r_[g[name + "/du"], 0])):
+            assert np.array_equal(mine == 0, ref == 0)
+            assert np.allclose(mine, ref, rtol=1e-5, atol=0)
+        assert np.array_equal(fac, g[name + "/factor"])
+        _, d2, _, fac2 = oracle.num_jac(col["x"], grp, col["par"], col["stat"], psi, nr, precip,
+                                        170, fac=fac)
+        assert np.array_equal(fac2, g[name + "/factor_second"])
+        assert np.allclose(d2, g[name + "/d_second"], rtol=1e-5, atol=0)
+
+
+def _teacher_forced(g, prefix, col, spinup):
+    grp, _ = pack.fd_groups(col["x"].size)
+    n = g[prefix + "y0"].shape[0]
+    errs, same, th_err, wtd_ok = [], [], [], []
+    for w in range(n):
+        nr = g[prefix + "n_rnd"][w].copy()
+        t0 = float(g[prefix + "t0"][w])
+        y, st, status, lat, t_acc = oracle.solve_window(
+            col["x"], grp, col["par"], col["stat"], t0, t0 + 1.0, g[prefix + "y0"][w], nr,
+            float(g[prefix + "precip"][w]), int(g[prefix + "wtd"][w]), 0, spinup)
+        ref = g[prefix + "y_end"][w]
+        assert status == int(g[prefix + "status"][w] != 0)
+        errs.append(tol_scaled(y, ref))
+        same.append(st["nfev"] == g[prefix + "nfev"][w] and st["njev"] == g[prefix + "njev"][w]
+                    and st["nlu"] == g[prefix + "nlu"][w] and st["nsteps"] == g[prefix + "nsteps"][w])
+        psi_sat = col["par"][pack.P_PSI_SAT]
+        wtd_ok.append(oracle.find_wtd(y >= psi_sat) == oracle.find_wtd(ref >= psi_sat))
+        th = oracle.closure_nodes(col["x"], col["par"], col["stat"], y, nr)[0][0]
+        th_ref = oracle.closure_nodes(col["x"], col["par"], col["stat"], ref, nr)[0][0]
+        th_err.append(float(np.max(np.abs(th - th_ref) / th_ref)))
+    return np.array(errs), np.array(same), np.array(th_err), np.array(wtd_ok)
+
+
+def test_windows_default_run_against_reference(golden):
+    """Teacher-forced RichardsPDE.solve parity on 150 windows of the default
+    run.  The integrator is sensitive to rounding (the FD Jacobian amplifies
+    1e-16 differences), so parity is stated in units of the
+    solver's own tolerance atol + rtol*|psi|:
+      * solver counters (nfev, njev, nlu, steps) identical in >= 95 % of windows
+      * psi within 0.1 tolerance units in >= 95 % of windows, always < 5
+      * theta relative error <= 1e-6 in >= 98 % of windows
+      * water-table node identical in every window."""
+    g = golden("windows_default.npz")
+    errs, same, th_err, wtd_ok = _teacher_forced(g, "", default_column(), 0)
+    assert same.mean() >= 0.95
+    assert np.mean(errs <= 0.1) >= 0.95 and errs.max() < 5.0
+    assert np.median(errs) < 1e-4
+    assert np.mean(th_err <= 1e-6) >= 0.98
+    assert wtd_ok.all()
+
+
+def test_windows_spinup_against_reference(golden):
+    """Spin-up windows (SPINUP flags) start from the saturated column and are
+    the stiffest: decision flips are more frequent there."""
+    g = golden("spinup_default.npz")
+    errs, same, th_err, wtd_ok = _teacher_forced(g, "", default_column(), 1)
+    assert same.mean() >= 0.75
+    assert np.median(errs) < 1e-2
+    assert wtd_ok.mean() >= 0.9
+
+
+@pytest.mark.parametrize("name", ["vg_strat", "vf_constant", "vf_linear", "vf_exponential",
+                                  "ens0", "ens1", "ens2", "mix3", "mix4", "mix5", "mix6", "lam2"])
+def test_windows_variants_against_reference(golden, name):
+    g = golden("windows_variants.npz")
+    col = column_from_json(g[f"{name}/params_json"])
+    errs, same, th_err, wtd_ok = _teacher_forced(g, name + "/", col, 0)
+    assert same.mean() >= 0.9
+    assert np.mean(errs <= 0.2) >= 0.9 and errs.max() < 5.0
+    assert wtd_ok.all()
+
+
+def test_windows_fine_grid_against_reference(golden):
+    g = golden("windows_fine.npz")
+    from hydromodel_b200.synthetic import default_params, synthetic_forcing, fine_grid_site
+    import tempfile, os
+    site = fine_grid_site(os.path.join(tempfile.mkdtemp(), "site.json"))
+    col = pack.pack_column(default_params(site), synthetic_forcing(365, stiff=True))
+    assert col["x"].size == 1001
+    errs, same, th_err, wtd_ok = _teacher_forced(g, "", col, 0)
+    assert same.mean() >= 0.6
+    assert np.mean(errs <= 0.5) >= 0.8
+
+
+def test_run_driver_matches_window_by_window(golden):
+    """orc_run_c (the free-running window loop with the noise-refresh rule of
+    simulation.py:599-602) reproduces the teacher-forced chain of solves."""
+    g = golden("windows_default.npz")
+    col = default_column()
+    grp, _ = pack.fd_groups(401)
+    T = 31
+    f = col["forcing"]
+    # rebuild the tape from the golden run: slot 0 = first draw, then refreshes
+    tape = [g["n_rnd"][0] if not (f["precipitation_cm"][1] > 0.5) else None]
+    base = None
+    slots = []
+    for i in range(1, T):
+        refreshed = f["precipitation_cm"][i] > 0.5 or i % 48 == 0
+        if refreshed:
+            slots.append(g["n_rnd"][i - 1])
+        elif base is None:
+            base = g["n_rnd"][i - 1]
+    tape = np.stack([base] + slots)
+    psi, wscal, fields, stats, used = oracle.run(
+        col["x"], grp, col["par"], col["stat"], f["precipitation_cm"][:T], f["wtd_idx"][:T],
+        f["daylight"][:T], f["atm"][:T], tape, g["ic"], out_stride=10)
+    assert used == tape.shape[0]
+    assert tol_scaled(psi, g["psi_press"][T - 1]) < 1.0
+    assert np.array_equal(wscal[:, 0] * 5.0, g["wtd_est_cm"][:T])
+    assert fields.shape[0] == 4
+    assert np.allclose(fields[1, 1], g["theta_vol"][10], rtol=1e-5)
