@@ -8,6 +8,7 @@
 //                   solve / single window for the parity tests
 //   philox_base_kernel, moments_kernel   noise initialisation, ensemble stats
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -80,8 +81,8 @@ __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row,
     }
 }
 
-template <int NT, int CPT>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
+template <int NT, int CPT, int MB>
+__global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
 {
     __shared__ int s_col;
     const int nx = c.nx, tid = threadIdx.x;
@@ -146,8 +147,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) run_kerne
     }
 }
 
-template <int NT, int CPT>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) spinup_kernel(const __grid_constant__ DevCtx c, int max_iter,
+template <int NT, int CPT, int MB>
+__global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ DevCtx c, int max_iter,
                                                                     const double *nrnd0, const double *zwtd0,
                                                                     int *iters_out)
 {
@@ -202,8 +203,8 @@ struct HookArgs {
 };
 enum { HK_RHS = 0, HK_NODES, HK_JAC, HK_TRI, HK_WINDOW };
 
-template <int NT, int CPT>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? HB_MIN_BLOCKS : 1)) hook_kernel(const __grid_constant__ DevCtx c, HookArgs h)
+template <int NT, int CPT, int MB>
+__global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ DevCtx c, HookArgs h)
 {
     const int nx = c.nx, tid = threadIdx.x;
     bind_column<NT>(c, h.col);
@@ -323,15 +324,25 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
     return 0;
 }
 
-#define DISPATCH(ctx, NAME, grid, ...)                                                     \
-    do {                                                                                   \
-        if ((ctx)->variant == 0)                                                           \
-            NAME<256, 2><<<grid, 256, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__);    \
-        else if ((ctx)->variant == 1)                                                      \
-            NAME<512, 2><<<grid, 512, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__);    \
-        else                                                                               \
-            NAME<512, 3><<<grid, 512, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__);    \
-        (ctx)->launches++;                                                                 \
+// Kernel variants: <threads per column, cells per thread, min CTAs per SM>.
+//   0: <256,2,2>  nx <= 512 (default)     3: <128,4,3>  nx <= 512, fewer/wider threads
+//   1: <512,2,1>  nx <= 1024              4: <256,2,3>  nx <= 512, 85-register cap
+//   2: <512,3,1>  nx <= 1320
+#define HB_FOR_VARIANT(ctx, STMT)                                   \
+    do {                                                            \
+        switch ((ctx)->variant) {                                   \
+        case 0: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; STMT; } break; \
+        case 1: { constexpr int NT_ = 512, CPT_ = 2, MB_ = 1; STMT; } break; \
+        case 2: { constexpr int NT_ = 512, CPT_ = 3, MB_ = 1; STMT; } break; \
+        case 3: { constexpr int NT_ = 128, CPT_ = 4, MB_ = 3; STMT; } break; \
+        default: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 3; STMT; } break; \
+        }                                                           \
+    } while (0)
+
+#define DISPATCH(ctx, NAME, grid, ...)                                                        \
+    do {                                                                                      \
+        HB_FOR_VARIANT(ctx, (NAME<NT_, CPT_, MB_><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
+        (ctx)->launches++;                                                                    \
     } while (0)
 
 extern "C" {
@@ -357,6 +368,10 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.nx = nx; d.nxp = (nx + 1) & ~1; d.n_cols = n_cols;
     d.rtol = 1e-3; d.atol = 1e-3;
     ctx->variant = nx <= 512 ? 0 : (nx <= 1024 ? 1 : 2);
+    if (const char *v = getenv("HB_VARIANT")) {          // tuning experiments
+        const int want = atoi(v);
+        if (nx <= 512 && (want == 0 || want == 3 || want == 4)) ctx->variant = want;
+    }
     ctx->smem_bytes = smem_doubles(d.nxp) * sizeof(double);
     {   // BDF coefficient tables exactly as scipy builds them (bdf.py:244-247)
         const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
@@ -390,16 +405,11 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.x = x; d.dx = dx; d.zx = zx; d.xz = xz; d.grp = grp; d.par = par; d.stat = stat;
     d.psi = psi; d.noise_base = nb; d.queue = queue; d.slot_next = slot; d.counters = cnt;
     d.noise_mode = HB_NOISE_TAPE; d.n_slots = 0; d.tape = nullptr;
-#define PREP(NT_, CPT_)                                                        \
-    do {                                                                       \
-        rc = prep_kernel(ctx, hook_kernel<NT_, CPT_>, NT_);                    \
-        if (!rc) rc = prep_kernel(ctx, spinup_kernel<NT_, CPT_>, NT_);         \
-        if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_>, NT_);            \
-    } while (0)
-    if (ctx->variant == 0) PREP(256, 2);
-    else if (ctx->variant == 1) PREP(512, 2);
-    else PREP(512, 3);
-#undef PREP
+    HB_FOR_VARIANT(ctx, {
+        rc = prep_kernel(ctx, hook_kernel<NT_, CPT_, MB_>, NT_);
+        if (!rc) rc = prep_kernel(ctx, spinup_kernel<NT_, CPT_, MB_>, NT_);
+        if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_, MB_>, NT_);
+    });
     if (rc) { hb_destroy(ctx); return nullptr; }
     return ctx;
 }

@@ -110,7 +110,7 @@ __device__ __forceinline__ double warp_sum(double v)
 // `parity` alternates between two slot sets so that back-to-back reductions
 // need no second barrier.
 template <int NT>
-__device__ __forceinline__ double block_sum(const DevCtx &c, int &parity, double v)
+__device__ __noinline__ double block_sum(const DevCtx &c, int &parity, double v)
 {
     v = warp_sum(v);
     double *r = HB_X(c, X_RED) + (parity << 5);
@@ -140,9 +140,18 @@ __device__ __forceinline__ int block_max_int(const DevCtx &c, int &parity, int v
 
 // RMS norm (SCIPY common.py:63-65) from this thread's partial sum of squares.
 template <int NT>
-__device__ __forceinline__ double rms(const DevCtx &c, int &parity, double local_sq)
+__device__ __noinline__ double rms(const DevCtx &c, int &parity, double local_sq)
 {
     return sqrt(block_sum<NT>(c, parity, local_sq)) / sqrt((double)c.nx);
+}
+
+// rate ** n for the small positive integers of the Newton convergence test
+// (python float ** int; bdf.py:56).
+__device__ __forceinline__ double ipow(double x, int n)
+{
+    double r = x;
+    for (int i = 1; i < n; ++i) r *= x;
+    return r;
 }
 
 struct Clos { double theta, K, C, kb; };
@@ -803,7 +812,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                     if (have_old) {
                         rate = dy_norm / dy_norm_old;
                         if (rate >= 1.0 ||
-                            pow(rate, (double)(HB_NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)
+                            ipow(rate, HB_NEWTON_MAXITER - k) / (1.0 - rate) * dy_norm > newton_tol)
                             break;
                     }
                     if (dy_norm == 0.0 || (have_old && rate / (1.0 - rate) * dy_norm < newton_tol)) {
