@@ -22,30 +22,23 @@
 
 using namespace hb;
 
-template <int NT>
-__device__ inline void bind_column(const DevCtx &c, int col)
+__device__ inline void add_counters(long long *dst, const long long *k, long long windows)
 {
-    for (int i = threadIdx.x; i < HB_NPARAM; i += NT)
-        HB_X(c, X_PAR)[i] = c.par[(size_t)col * HB_NPARAM + i];
-}
-
-__device__ inline void add_counters(long long *dst, const Counters &k, long long windows)
-{
-    dst[HB_C_NFEV] += k.nfev; dst[HB_C_NJEV] += k.njev; dst[HB_C_NLU] += k.nlu;
-    dst[HB_C_NSTEPS] += k.nsteps; dst[HB_C_NREJECT] += k.nreject; dst[HB_C_NFAIL] += k.nfail;
-    dst[HB_C_NRHS] += k.nrhs; dst[HB_C_NNEWTON] += k.nnewton; dst[HB_C_NWINDOWS] += windows;
+    dst[HB_C_NFEV] += k[K_NFEV]; dst[HB_C_NJEV] += k[K_NJEV]; dst[HB_C_NLU] += k[K_NLU];
+    dst[HB_C_NSTEPS] += k[K_NSTEPS]; dst[HB_C_NREJECT] += k[K_NREJECT]; dst[HB_C_NFAIL] += k[K_NFAIL];
+    dst[HB_C_NRHS] += k[K_NRHS]; dst[HB_C_NNEWTON] += k[K_NNEWTON]; dst[HB_C_NWINDOWS] += windows;
 }
 
 // Closure on the nodes at the state in V_Y with the noise in V_NR (the
 // diagnostic call of simulation.py:564,623: node k uses n_rnd[k]).
-template <int NT>
+template <int NT, int NV>
 __device__ inline void nodes_diag(const DevCtx &c, int col, double *th, double *K, double *C, double *kb)
 {
     const int nx = c.nx;
     const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
     for (int k = threadIdx.x; k < nx; k += NT) {
         Clos r;
-        closure_cold(HB_X(c, X_PAR), HB_VEC(c, V_Y)[k], st[(size_t)HB_S_PHI_NODE * nx + k],
+        closure_cold(HB_XA(c, NV, X_PAR), HB_VEC(c, V_Y)[k], st[(size_t)HB_S_PHI_NODE * nx + k],
                      st[(size_t)HB_S_KMEAN_NODE * nx + k], st[(size_t)HB_S_COEF_NODE * nx + k],
                      HB_VEC(c, V_NR)[k], &r);
         th[k] = r.theta; K[k] = r.K; kb[k] = r.kb;
@@ -56,7 +49,7 @@ __device__ inline void nodes_diag(const DevCtx &c, int col, double *th, double *
 // Diagnostics of one row: estimated water table, lateral flow of the last RHS
 // evaluation (arg_out, quirk Q6) and, on output rows, the closure on the nodes
 // (simulation.py:612-630).  State is in V_Y.
-template <int NT>
+template <int NT, int NV>
 __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row, int status, bool solved)
 {
     const int nx = c.nx, tid = threadIdx.x;
@@ -65,10 +58,10 @@ __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row,
         if (tid == 0) { ws[HB_W_WTD_EST] = 0.0; ws[HB_W_LATERAL] = 0.0; ws[HB_W_TRANSP] = 0.0; ws[HB_W_STATUS] = 2.0; }
         return;
     }
-    const int wtd_est = find_wtd_nodes<NT>(c, parity, HB_VEC(c, V_Y));
+    const int wtd_est = find_wtd_nodes<NT, NV>(c, parity, HB_VEC(c, V_Y));
     if (tid == 0) {
         ws[HB_W_WTD_EST] = (double)wtd_est;
-        ws[HB_W_LATERAL] = solved ? lateral_flow<NT>(c) : 0.0;
+        ws[HB_W_LATERAL] = solved ? lateral_flow<NT, NV>(c) : 0.0;
         ws[HB_W_TRANSP] = 0.0;
         ws[HB_W_STATUS] = (double)status;
     }
@@ -76,14 +69,15 @@ __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row,
         const int o = (row % c.out_stride == 0) ? row / c.out_stride : c.n_out - 1;
         double *f = c.fields + ((size_t)col * c.n_out + o) * HB_NFIELD * nx;
         for (int k = tid; k < nx; k += NT) f[(size_t)HB_F_PSI * nx + k] = HB_VEC(c, V_Y)[k];
-        nodes_diag<NT>(c, col, f + (size_t)HB_F_THETA * nx, f + (size_t)HB_F_K * nx, nullptr,
-                       f + (size_t)HB_F_KBKG * nx);
+        nodes_diag<NT, NV>(c, col, f + (size_t)HB_F_THETA * nx, f + (size_t)HB_F_K * nx, nullptr,
+                           f + (size_t)HB_F_KBKG * nx);
     }
 }
 
-template <int NT, int CPT, int MB>
+template <int NT, int CPT, int MB, bool FULL>
 __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
 {
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     __shared__ int s_col;
     const int nx = c.nx, tid = threadIdx.x;
     double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
@@ -94,13 +88,12 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
         __syncthreads();
         const int col = s_col;
         if (col >= c.n_cols) break;
-        bind_column<NT>(c, col);
+        bind_column<NT, FULL>(c, col);
         double *psi_g = c.psi + (size_t)col * nx;
         double *nb = c.noise_base + (size_t)col * nx;
         for (int i = tid; i < nx; i += NT) { nr[i] = nb[i]; y[i] = psi_g[i]; }
         bool nr_is_base = true;
         const int ser = c.series ? c.series[col] : 0;
-        Counters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
         long long windows = 0;
         __syncthreads();
         for (int row = w0; row < w1; ++row) {
@@ -110,7 +103,7 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
                 const int wtd = c.wtd_idx[(size_t)ser * c.T + row];
                 if (wtd < 0) status = 2;
                 else {
-                    const double p = HB_X(c, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
+                    const double p = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
                     const bool refresh = (p > 0.5) || (row % 48 == 0);   // simulation.py:599
                     __syncthreads();
                     if (refresh) {
@@ -134,24 +127,28 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
                     a.precip = p; a.wtd = wtd;
                     a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
                     bool damped = false;
-                    status = solve_window<NT, CPT>(c, col, a, (double)(row - 1), (double)row, psi_g, cnt, damped);
+                    status = solve_window<NT, CPT, FULL>(c, col, a, (double)(row - 1), (double)row, psi_g, damped);
                     if (damped && nr_is_base)
                         for (int i = tid; i < nx; i += NT) nb[i] = nr[i];
                     for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
                     windows++; solved = true;
                 }
             }
-            write_row<NT>(c, parity, col, row, status, solved);
+            write_row<NT, NV>(c, parity, col, row, status, solved);
         }
-        if (tid == 0) add_counters(c.counters + (size_t)col * HB_NCOUNTER, cnt, windows);
+        __syncthreads();
+        if (tid == 0)
+            add_counters(c.counters + (size_t)col * HB_NCOUNTER,
+                         reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), windows);
     }
 }
 
-template <int NT, int CPT, int MB>
+template <int NT, int CPT, int MB, bool FULL>
 __global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ DevCtx c, int max_iter,
-                                                                    const double *nrnd0, const double *zwtd0,
-                                                                    int *iters_out)
+                                                         const double *nrnd0, const double *zwtd0,
+                                                         int *iters_out)
 {
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     __shared__ int s_col;
     const int nx = c.nx, tid = threadIdx.x;
     double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
@@ -162,7 +159,7 @@ __global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ 
         __syncthreads();
         const int col = s_col;
         if (col >= c.n_cols) break;
-        bind_column<NT>(c, col);
+        bind_column<NT, FULL>(c, col);
         double *psi_g = c.psi + (size_t)col * nx;
         for (int i = tid; i < nx; i += NT)
             nr[i] = nrnd0 ? nrnd0[(size_t)col * nx + i]
@@ -170,24 +167,25 @@ __global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ 
         const int ser = c.series ? c.series[col] : 0;
         __syncthreads();
         Args a;
-        a.precip = HB_X(c, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T];
+        a.precip = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T];
         a.wtd = c.wtd_idx[(size_t)ser * c.T]; a.mode = 2;
-        const double dz = HB_X(c, X_PAR)[HB_P_DZ];
-        Counters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
+        const double dz = HB_XA(c, NV, X_PAR)[HB_P_DZ];
         int it = 0;
         for (it = 0; it < max_iter; ++it) {
             bool damped = false;
-            solve_window<NT, CPT>(c, col, a, 0.0, 1.0, psi_g, cnt, damped);
-            const int wtd_est = find_wtd_nodes<NT>(c, parity, y);
+            solve_window<NT, CPT, FULL>(c, col, a, 0.0, 1.0, psi_g, damped);
+            const int wtd_est = find_wtd_nodes<NT, NV>(c, parity, y);
             const double abs_err = fabs(zwtd0[col] - c.x[wtd_est]);
             double loc = 0.0;
             for (int i = tid; i < nx; i += NT) { const double dl = y[i] - psi_g[i]; loc += dl * dl; }
-            const double mse = block_sum<NT>(c, parity, loc) / (double)nx;
+            const double mse = block_sum<NT, NV>(c, parity, loc) / (double)nx;
             for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
             if (abs_err <= 2.0 * dz && mse <= 0.01) { it++; break; }
         }
+        __syncthreads();
         if (tid == 0) {
-            add_counters(c.counters + (size_t)col * HB_NCOUNTER, cnt, it);
+            add_counters(c.counters + (size_t)col * HB_NCOUNTER,
+                         reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), it);
             if (iters_out) iters_out[col] = it;
         }
     }
@@ -203,28 +201,30 @@ struct HookArgs {
 };
 enum { HK_RHS = 0, HK_NODES, HK_JAC, HK_TRI, HK_WINDOW };
 
-template <int NT, int CPT, int MB>
+template <int NT, int CPT, int MB, bool FULL>
 __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ DevCtx c, HookArgs h)
 {
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     const int nx = c.nx, tid = threadIdx.x;
-    bind_column<NT>(c, h.col);
+    bind_column<NT, FULL>(c, h.col);
     double *io = h.io;
     double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR), *b = HB_VEC(c, V_B);
     Args a;
     a.precip = h.precip; a.wtd = h.wtd; a.mode = h.spinup ? 2 : (h.daylight ? 1 : 0);
-    Counters cnt = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = tid; i < nx; i += NT) { y[i] = io[i]; nr[i] = io[nx + i]; }
     __syncthreads();
     if (h.mode == HK_RHS) {
-        rhs_eval<NT, CPT>(c, h.col, a.precip, a.wtd, a.mode, V_B);
+        const Statics S = statics_of<FULL>(c, h.col);
+        rhs_eval<NT, CPT, NV>(c, S, a.precip, a.wtd, a.mode, V_B);
         for (int i = tid; i < nx; i += NT) io[2 * nx + i] = b[i];
         __syncthreads();
-        if (tid == 0) io[3 * nx] = lateral_flow<NT>(c);
+        if (tid == 0) io[3 * nx] = lateral_flow<NT, NV>(c);
     } else if (h.mode == HK_NODES) {
-        nodes_diag<NT>(c, h.col, io + 2 * nx, io + 3 * nx, io + 4 * nx, io + 5 * nx);
+        nodes_diag<NT, NV>(c, h.col, io + 2 * nx, io + 3 * nx, io + 4 * nx, io + 5 * nx);
     } else if (h.mode == HK_JAC) {
-        for (int i = tid; i < nx; i += NT) { b[i] = io[i]; if (!h.first) HB_VEC(c, V_FAC)[i] = io[2 * nx + i]; }
-        num_jac<NT, CPT>(c, h.col, a.precip, a.wtd, a.mode, V_B, h.first != 0, cnt);
+        // the production state machine, stopped right after the initial Jacobian
+        if (!h.first) for (int i = tid; i < nx; i += NT) HB_VEC(c, V_FAC)[i] = io[2 * nx + i];
+        bdf_attempt<NT, CPT, FULL>(c, h.col, a.precip, a.wtd, a.mode, 0.0, 1.0, io, h.first ? 1 : 2);
         for (int i = tid; i < nx; i += NT) {
             io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
             io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_VEC(c, V_FAC)[i];
@@ -235,18 +235,18 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
             HB_VEC(c, V_JU)[i] = io[4 * nx + i]; b[i] = io[5 * nx + i];
         }
         __syncthreads();
-        if (tid < 32) { tri_factor(c, h.c); tri_solve(c, h.c); }
+        if (tid < 32) { tri_factor<NV>(c, h.c); tri_solve<NV>(c, h.c); }
         __syncthreads();
         for (int i = tid; i < nx; i += NT) io[6 * nx + i] = b[i];
     } else if (h.mode == HK_WINDOW) {
         bool damped = false;
-        const int st = solve_window<NT, CPT>(c, h.col, a, h.t0, h.t1, io, cnt, damped);
+        const int st = solve_window<NT, CPT, FULL>(c, h.col, a, h.t0, h.t1, io, damped);
         for (int i = tid; i < nx; i += NT) { io[2 * nx + i] = y[i]; io[nx + i] = nr[i]; }
         __syncthreads();
         if (tid == 0) {
-            io[3 * nx] = lateral_flow<NT>(c);
+            io[3 * nx] = lateral_flow<NT, NV>(c);
             long long z[HB_NCOUNTER] = {0};
-            add_counters(z, cnt, 1);
+            add_counters(z, reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), 1);
             for (int k = 0; k < HB_NCOUNTER; ++k) h.stats[k] = z[k];
             h.stats[HB_NCOUNTER] = st;
         }
@@ -324,24 +324,25 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
     return 0;
 }
 
-// Kernel variants: <threads per column, cells per thread, min CTAs per SM>.
-//   0: <256,2,2>  nx <= 512 (default)     3: <128,4,3>  nx <= 512, fewer/wider threads
-//   1: <512,2,1>  nx <= 1024              4: <256,2,3>  nx <= 512, 85-register cap
-//   2: <512,3,1>  nx <= 1320
+// Kernel variants: <threads per column, cells per thread, min CTAs per SM,
+// FULL = static profiles and grid metrics staged in shared memory>.
+//   0: <256,2,2,true>   nx <= 464 (default)
+//   1: <256,2,2,false>  nx <= 512
+//   2: <512,2,1,false>  nx <= 1024
+//   3: <512,3,1,false>  nx <= 1152
 #define HB_FOR_VARIANT(ctx, STMT)                                   \
     do {                                                            \
         switch ((ctx)->variant) {                                   \
-        case 0: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; STMT; } break; \
-        case 1: { constexpr int NT_ = 512, CPT_ = 2, MB_ = 1; STMT; } break; \
-        case 2: { constexpr int NT_ = 512, CPT_ = 3, MB_ = 1; STMT; } break; \
-        case 3: { constexpr int NT_ = 128, CPT_ = 4, MB_ = 3; STMT; } break; \
-        default: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 3; STMT; } break; \
+        case 0: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; constexpr bool FL_ = true; STMT; } break;  \
+        case 1: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; constexpr bool FL_ = false; STMT; } break; \
+        case 2: { constexpr int NT_ = 512, CPT_ = 2, MB_ = 1; constexpr bool FL_ = false; STMT; } break; \
+        default: { constexpr int NT_ = 512, CPT_ = 3, MB_ = 1; constexpr bool FL_ = false; STMT; } break; \
         }                                                           \
     } while (0)
 
 #define DISPATCH(ctx, NAME, grid, ...)                                                        \
     do {                                                                                      \
-        HB_FOR_VARIANT(ctx, (NAME<NT_, CPT_, MB_><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
+        HB_FOR_VARIANT(ctx, (NAME<NT_, CPT_, MB_, FL_><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
         (ctx)->launches++;                                                                    \
     } while (0)
 
@@ -349,7 +350,7 @@ extern "C" {
 
 const char *hb_last_error(void) { return g_err.c_str(); }
 int hb_version(void) { return 100; }
-int hb_max_nx(void) { return 1320; }
+int hb_max_nx(void) { return 1152; }
 
 hb_ctx *hb_create(int device, int nx, int n_cols)
 {
@@ -367,12 +368,12 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     DevCtx &d = ctx->d;
     d.nx = nx; d.nxp = (nx + 1) & ~1; d.n_cols = n_cols;
     d.rtol = 1e-3; d.atol = 1e-3;
-    ctx->variant = nx <= 512 ? 0 : (nx <= 1024 ? 1 : 2);
+    ctx->variant = nx <= 464 ? 0 : (nx <= 512 ? 1 : (nx <= 1024 ? 2 : 3));
     if (const char *v = getenv("HB_VARIANT")) {          // tuning experiments
         const int want = atoi(v);
-        if (nx <= 512 && (want == 0 || want == 3 || want == 4)) ctx->variant = want;
+        if (nx <= 512 && want == 1) ctx->variant = 1;
     }
-    ctx->smem_bytes = smem_doubles(d.nxp) * sizeof(double);
+    ctx->smem_bytes = smem_doubles(d.nxp, ctx->variant == 0) * sizeof(double);
     {   // BDF coefficient tables exactly as scipy builds them (bdf.py:244-247)
         const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
         double gam[6], alp[6], erc[6];
@@ -406,9 +407,9 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.psi = psi; d.noise_base = nb; d.queue = queue; d.slot_next = slot; d.counters = cnt;
     d.noise_mode = HB_NOISE_TAPE; d.n_slots = 0; d.tape = nullptr;
     HB_FOR_VARIANT(ctx, {
-        rc = prep_kernel(ctx, hook_kernel<NT_, CPT_, MB_>, NT_);
-        if (!rc) rc = prep_kernel(ctx, spinup_kernel<NT_, CPT_, MB_>, NT_);
-        if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_, MB_>, NT_);
+        rc = prep_kernel(ctx, hook_kernel<NT_, CPT_, MB_, FL_>, NT_);
+        if (!rc) rc = prep_kernel(ctx, spinup_kernel<NT_, CPT_, MB_, FL_>, NT_);
+        if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_, MB_, FL_>, NT_);
     });
     if (rc) { hb_destroy(ctx); return nullptr; }
     return ctx;

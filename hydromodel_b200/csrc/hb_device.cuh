@@ -2,20 +2,24 @@
 //
 // Mapping: one CTA integrates one soil column.  Cell i of the column belongs to
 // thread (i % NT); all per-column vectors (BDF difference table, tridiagonal
-// Jacobian and its factors, Newton iterate, noise field) live in shared memory
-// in natural order, so neighbour access is a conflict-free shared load and
-// every element-wise update is private to the owning thread.  Scalars of the
-// step controller (h, order, norms ...) are computed redundantly by every
-// thread from block-wide reductions, which keeps control flow CTA-uniform
-// without broadcasts.  The tridiagonal Newton systems are solved by warp 0 with
-// a partition (chunked Thomas) / warp-shuffle PCR hybrid.
+// Jacobian and its factors, Newton iterate, noise field, static profiles) live
+// in shared memory in natural order, so neighbour access is a conflict-free
+// shared load and every element-wise update is private to the owning thread.
+// Scalars of the step controller (h, order, norms ...) are computed redundantly
+// by every thread from block-wide reductions, which keeps control flow
+// CTA-uniform without broadcasts.  The tridiagonal Newton systems are solved by
+// warp 0 with a partition (chunked Thomas) / warp-shuffle PCR hybrid.
+//
+// The integrator is written as ONE loop around ONE inlined right-hand-side
+// evaluation (a state machine): the instruction footprint of the hot loop is
+// what bounds this kernel, not arithmetic (profiles/).
 //
 // Reference arithmetic reproduced (paths relative to /root/reference/code/src;
 // SCIPY = scipy/integrate/_ivp of scipy 1.18.1, the package the reference calls):
 //   closure()            models/vrettas_fung.py:108-249, models/vanGenuchten.py:71-117,
 //                        utilities.py:4-54
 //   rhs_eval()           richards_pde.py:82-160, :198-204, :306-376, :414-476, :542-595
-//   num_jac()            SCIPY common.py:268-341,385-455
+//   jacobian states      SCIPY common.py:268-341,385-455 (num_jac, grouped columns)
 //   tri_factor/solve()   in place of splu / LU.solve, SCIPY bdf.py:222-227
 //   change_D()           SCIPY bdf.py:18-33
 //   bdf_attempt()        SCIPY bdf.py:36-69,198-256,314-455; common.py:63-134;
@@ -54,17 +58,21 @@ namespace hb {
 
 extern __shared__ double smem[];
 
-// ---- shared-memory layout: NVEC vectors of nxp doubles, then a small area ---
+// ---- shared-memory layout: vectors of nxp doubles, then a small area --------
 enum {
     V_D = 0,                // D[0..7]: BDF difference table
     V_JL = 8, V_JD, V_JU,   // Jacobian rows: lower, diagonal, upper
-    V_TW, V_TIP, V_TVL, V_TVR,   // tridiagonal factors (num_jac scratch as well)
+    V_TW, V_TIP, V_TVL, V_TVR,   // tridiagonal factors (Jacobian scratch as well)
     V_Y,                    // Newton iterate / RHS input
     V_CM, V_FM,             // RHS scratch: C and flux at the midpoints
     V_B,                    // linear-system rhs / solution, RHS output
     V_FAC,                  // num_jac step factors
     V_NR,                   // noise field n_rnd of the current window
-    NVEC
+    V_PSI, V_SCL, V_DD,     // Newton: psi, scale, accumulated correction d
+    NVEC_BASE,              // = 24
+    V_PHI = NVEC_BASE, V_KM, V_CF,   // static profiles at the midpoints   (FULL only)
+    V_DX, V_ZX, V_XZ,                // grid metrics                       (FULL only)
+    NVEC_FULL               // = 30
 };
 enum {                      // offsets (doubles) inside the small area
     X_RED = 0,              // [2][32] block-reduction slots
@@ -74,20 +82,21 @@ enum {                      // offsets (doubles) inside the small area
     X_MISC = 516 + HB_NPARAM,    // [8]  0: p_left
     X_LATW = X_MISC + 8,    // [32] per-warp lateral-flow partial sums
     X_WMAX = X_LATW + 32,   // [32 ints] deepest unsaturated midpoint per warp
-    X_END = X_WMAX + 16
+    X_CNT = X_WMAX + 16,    // [8 long long] solver counters (thread 0 writes)
+    X_END = X_CNT + 8
 };
+enum { K_NFEV = 0, K_NJEV, K_NLU, K_NSTEPS, K_NREJECT, K_NFAIL, K_NRHS, K_NNEWTON };
 
-__host__ __device__ inline size_t smem_doubles(int nxp) { return (size_t)NVEC * nxp + X_END; }
+__host__ __device__ inline size_t smem_doubles(int nxp, bool full)
+{
+    return (size_t)(full ? NVEC_FULL : NVEC_BASE) * nxp + X_END;
+}
 
 #define HB_VEC(c, k) (hb::smem + (size_t)(k) * (c).nxp)
-#define HB_X(c, off) (hb::smem + (size_t)hb::NVEC * (c).nxp + (off))
+#define HB_XA(c, NV, off) (hb::smem + (size_t)(NV) * (c).nxp + (off))
 
-struct Counters {
-    long long nfev, njev, nlu, nsteps, nreject, nfail, nrhs, nnewton;
-};
-
-// args_i of simulation.py:591-596 in device form; bit 0 of `mode`: daylight,
-// bit 1: SPINUP.
+// args_i of simulation.py:591-596 in device form; mode: 0 night, 1 daylight
+// (surface evaporation may act), 2 SPINUP.
 struct Args {
     double precip;          // already scaled by the column's multiplier
     int wtd;                // observed water-table node index
@@ -109,11 +118,11 @@ __device__ __forceinline__ double warp_sum(double v)
 // Sum over the CTA, identical in every thread.  Contains one __syncthreads().
 // `parity` alternates between two slot sets so that back-to-back reductions
 // need no second barrier.
-template <int NT>
-__device__ __noinline__ double block_sum(const DevCtx &c, int &parity, double v)
+template <int NT, int NV>
+__device__ __forceinline__ double block_sum(const DevCtx &c, int &parity, double v)
 {
     v = warp_sum(v);
-    double *r = HB_X(c, X_RED) + (parity << 5);
+    double *r = HB_XA(c, NV, X_RED) + (parity << 5);
     parity ^= 1;
     if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -123,12 +132,12 @@ __device__ __noinline__ double block_sum(const DevCtx &c, int &parity, double v)
     return acc;
 }
 
-template <int NT>
-__device__ __forceinline__ int block_max_int(const DevCtx &c, int &parity, int v)
+template <int NT, int NV>
+__device__ __noinline__ int block_max_int(const DevCtx &c, int &parity, int v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(HB_FULL, v, o));
-    int *r = reinterpret_cast<int *>(HB_X(c, X_RED) + (parity << 5));
+    int *r = reinterpret_cast<int *>(HB_XA(c, NV, X_RED) + (parity << 5));
     parity ^= 1;
     if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -139,10 +148,10 @@ __device__ __forceinline__ int block_max_int(const DevCtx &c, int &parity, int v
 }
 
 // RMS norm (SCIPY common.py:63-65) from this thread's partial sum of squares.
-template <int NT>
+template <int NT, int NV>
 __device__ __noinline__ double rms(const DevCtx &c, int &parity, double local_sq)
 {
-    return sqrt(block_sum<NT>(c, parity, local_sq)) / sqrt((double)c.nx);
+    return sqrt(block_sum<NT, NV>(c, parity, local_sq)) / sqrt((double)c.nx);
 }
 
 // rate ** n for the small positive integers of the Newton convergence test
@@ -154,7 +163,33 @@ __device__ __forceinline__ double ipow(double x, int n)
     return r;
 }
 
+// x ** (-1/q) for the step-size factors (bdf.py:399,444), out of line: cold.
+__device__ __noinline__ double inv_root(double x, int q)
+{
+    return pow(x, -1.0 / q);
+}
+
+// Out-of-line IEEE double helpers.  The hot loop of this kernel is bound by
+// its instruction footprint (profiles/): every inlined FP64 division, sqrt, exp
+// or log costs 25-70 SASS instructions per call site, a call costs one.
+__device__ __noinline__ double hb_div(double a, double b) { return a / b; }
+__device__ __noinline__ double hb_sqrt(double a) { return sqrt(a); }
+__device__ __noinline__ double hb_exp(double a) { return exp(a); }
+__device__ __noinline__ double hb_log(double a) { return log(a); }
+
 struct Clos { double theta, K, C, kb; };
+
+// Rare branches of the closure, out of line: van Genuchten-Mualem conductivity
+// (vanGenuchten.py:91-104) and a general lambda exponent (vrettas_fung.py:229).
+__device__ __noinline__ double closure_rare_K(const double *par, double s_eff, double base,
+                                              double kb, bool vg)
+{
+    const double n = par[HB_P_N], m = par[HB_P_M];
+    if (!vg) return pow(s_eff, par[HB_P_LAMBDA]) * kb;
+    const double mth = 1.0 / base;
+    const double u = 1.0 - ((n == 2.0) ? sqrt(1.0 - mth) : pow(1.0 - mth, m));
+    return kb * sqrt(s_eff) * ((n == 2.0) ? u * u : pow(u, n));
+}
 
 // One closure evaluation.  Same map as the reference's VrettasFung /
 // vanGenuchten __call__, with the power functions composed from one shared
@@ -181,105 +216,148 @@ __device__ __forceinline__ Clos closure(const double *par, double psi, double ph
     const double ax = alpha * fabs(psi);
     double xn, base, X;
     if (n == 2.0) {
-        xn = ax * ax; base = 1.0 + xn; X = 1.0 / sqrt(base);
+        xn = ax * ax; base = 1.0 + xn; X = hb_div(1.0, hb_sqrt(base));
     } else {
-        xn = exp(n * log(ax)); base = 1.0 + xn; X = exp(-m * log(base));
+        xn = hb_exp(n * hb_log(ax)); base = 1.0 + xn; X = hb_exp(-m * hb_log(base));
     }
     const double q = th_r + delta_s * X;
-    const double s_eff = fmin(fmax((q - th_r) / delta_s, 0.0), 1.0);
-    double K, kb;
-    if (!vg) {
-        const double selam = (lam == 1.0) ? s_eff : (lam == 2.0 ? s_eff * s_eff : pow(s_eff, lam));
-        kb = ksoil;
-        if (coef >= 0.0) {
-            const double mean = (kmean == 0.0) ? 1.0e-7 : kmean;
-            const double var = par[HB_P_SIGMA] * (1.0 - s_eff);
-            const double l1 = log(var / (mean * mean) + 1.0);
-            kb = mean * exp(-0.5 * l1 + sqrt(l1) * (coef * e));
-        }
-        K = selam * kb;
-    } else {
-        const double mth = 1.0 / base;
-        const double u = 1.0 - ((n == 2.0) ? sqrt(1.0 - mth) : pow(1.0 - mth, m));
-        kb = ksoil;
-        K = kb * sqrt(s_eff) * ((n == 2.0) ? u * u : pow(u, n));
+    const double s_eff = fmin(fmax(hb_div(q - th_r, delta_s), 0.0), 1.0);
+    double K, kb = ksoil;
+    if (!vg && coef >= 0.0) {
+        const double mean = (kmean == 0.0) ? 1.0e-7 : kmean;
+        const double var = par[HB_P_SIGMA] * (1.0 - s_eff);
+        const double l1 = hb_log(hb_div(var, mean * mean) + 1.0);
+        kb = mean * hb_exp(-0.5 * l1 + hb_sqrt(l1) * (coef * e));
     }
+    if (vg || (lam != 1.0 && lam != 2.0)) K = closure_rare_K(par, s_eff, base, kb, vg);
+    else K = ((lam == 1.0) ? s_eff : s_eff * s_eff) * kb;
     K = fmin(K, kb);
-    double C = (m * n) * alpha * delta_s * (s_eff / base) * (xn / ax);
+    double C = (m * n) * alpha * delta_s * hb_div(s_eff, base) * hb_div(xn, ax);
     if (C < par[HB_P_EPS] || !isfinite(C)) C = par[HB_P_EPS];
     r.theta = q; r.K = K; r.C = C; r.kb = kb;
     return r;
 }
 
-// Out-of-line copy for the cold call sites (boundary closure, diagnostics).
+// Out-of-line copy for the diagnostics on the nodes (cold).
 __device__ __noinline__ void closure_cold(const double *par, double psi, double phi, double kmean,
                                           double coef, double e, Clos *out)
 {
     *out = closure(par, psi, phi, kmean, coef, e);
 }
 
+// Pointers to the static per-cell inputs of the right-hand side: shared memory
+// in the FULL layout, global memory (L1/L2) otherwise.
+struct Statics {
+    const double *phi, *km, *cf, *dx, *zx, *xz;
+};
+
+template <bool FULL>
+__device__ __forceinline__ Statics statics_of(const DevCtx &c, int col)
+{
+    Statics s;
+    if (FULL) {
+        s.phi = HB_VEC(c, V_PHI); s.km = HB_VEC(c, V_KM); s.cf = HB_VEC(c, V_CF);
+        s.dx = HB_VEC(c, V_DX); s.zx = HB_VEC(c, V_ZX); s.xz = HB_VEC(c, V_XZ);
+    } else {
+        const double *st = c.stat + (size_t)col * HB_NSTATIC * c.nx;
+        s.phi = st + (size_t)HB_S_PHI_MID * c.nx; s.km = st + (size_t)HB_S_KMEAN_MID * c.nx;
+        s.cf = st + (size_t)HB_S_COEF_MID * c.nx;
+        s.dx = c.dx; s.zx = c.zx; s.xz = c.xz;
+    }
+    return s;
+}
+
+// Stage one column: scalars, and in the FULL layout the static profiles and
+// grid metrics.  Caller synchronises afterwards.
+template <int NT, bool FULL>
+__device__ inline void bind_column(const DevCtx &c, int col)
+{
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
+    for (int i = threadIdx.x; i < HB_NPARAM; i += NT)
+        HB_XA(c, NV, X_PAR)[i] = c.par[(size_t)col * HB_NPARAM + i];
+    if (threadIdx.x < 8) reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT))[threadIdx.x] = 0;
+    if (FULL) {
+        const int nx = c.nx;
+        const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
+        for (int i = threadIdx.x; i < nx; i += NT) {
+            HB_VEC(c, V_PHI)[i] = st[(size_t)HB_S_PHI_MID * nx + i];
+            HB_VEC(c, V_KM)[i] = st[(size_t)HB_S_KMEAN_MID * nx + i];
+            HB_VEC(c, V_CF)[i] = st[(size_t)HB_S_COEF_MID * nx + i];
+            HB_VEC(c, V_DX)[i] = c.dx[i]; HB_VEC(c, V_ZX)[i] = c.zx[i]; HB_VEC(c, V_XZ)[i] = c.xz[i];
+        }
+    }
+}
+
+// Surface evaporation of bc_fun (richards_pde.py:455-468), daylight only: it
+// acts when np.all(theta_left > theta_res) over the profile the porosity call
+// broadcasts to (quirk Q2).  Cold: daily forcing never reaches it.
+__device__ __noinline__ double evaporation(const double *par, double y0)
+{
+    const double th_r = par[HB_P_THETA_RES];
+    const double ax = par[HB_P_ALPHA] * fabs(y0);
+    const double X = (par[HB_P_N] == 2.0) ? 1.0 / sqrt(1.0 + ax * ax)
+                                           : pow(1.0 + pow(ax, par[HB_P_N]), -par[HB_P_M]);
+    const bool sat0 = y0 >= par[HB_P_PSI_SAT];
+    const double dsm = sat0 ? par[HB_P_DSMIN_EXCL0] : par[HB_P_DSMIN_ALL];
+    if ((th_r + dsm * X > th_r) && (!sat0 || par[HB_P_PHI_TOP] > th_r)) return par[HB_P_SURF_EVAP];
+    return 0.0;
+}
+
 // dpsi/dt at the state held in vector V_Y (must be visible: caller
 // synchronises before the call).  The result is written to vector `out`
 // (each thread writes, and may afterwards read, its own cells).  Contains one
 // __syncthreads(); writes V_CM, V_FM and the small slots WMAX, MISC, LATW.
-template <int NT, int CPT>
-__device__ __noinline__ void rhs_eval(const DevCtx &c, int col, double precip, int wtd,
-                                      int mode, int out)
+template <int NT, int CPT, int NV>
+__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, double precip, int wtd,
+                                         int mode, int out)
 {
     const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double *par = HB_X(c, X_PAR);
+    const double *par = HB_XA(c, NV, X_PAR);
     const double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR);
     double *cm = HB_VEC(c, V_CM), *fm = HB_VEC(c, V_FM);
     const double psi_sat = par[HB_P_PSI_SAT];
-    const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
     int deepest = -1;                    // deepest unsaturated interior midpoint of this warp
 
     // ---- phase A: closures and fluxes at the midpoints ----------------------
+    // The top-boundary closure (bc_fun: (y[0], z = x[0])) rides along as one
+    // extra cell of the last thread in the last round, where that thread has no
+    // midpoint of its own (nx <= NT*CPT), so the closure code exists only once.
 #pragma unroll 1
     for (int r = 0; r < CPT; ++r) {
         const int k = tid + r * NT;
+        const bool bnd = (r == CPT - 1) && (tid == NT - 1);
         bool unsat_interior = false;
-        if (k < nx - 1) {
-            const double y0 = y[k], y1 = y[k + 1];
-            const double ym = 0.5 * (y0 + y1);
-            const double dy = (y1 - y0) / c.dx[k];
-            // noise index is local to the array handed to the closure (quirk Q1)
-            const double e = nr[k == 0 ? 0 : k - 1];
-            Clos cl = closure(par, ym, st[(size_t)HB_S_PHI_MID * nx + k],
-                              st[(size_t)HB_S_KMEAN_MID * nx + k],
-                              st[(size_t)HB_S_COEF_MID * nx + k], e);
-            cm[k] = cl.C;
-            fm[k] = cl.K * (dy - 1.0);
-            unsat_interior = (k >= 1) && !(ym >= psi_sat);
+        if (k < nx - 1 || bnd) {
+            double ym, dy = 0.0, e, phi, km, cf;
+            if (bnd) {
+                ym = y[0]; e = nr[0];
+                phi = par[HB_P_PHI_TOP]; km = par[HB_P_KMEAN_TOP]; cf = par[HB_P_COEF_TOP];
+            } else {
+                const double y0 = y[k], y1 = y[k + 1];
+                ym = 0.5 * (y0 + y1);
+                dy = hb_div(y1 - y0, S.dx[k]);
+                // noise index is local to the array handed to the closure (quirk Q1)
+                e = nr[k == 0 ? 0 : k - 1];
+                phi = S.phi[k]; km = S.km[k]; cf = S.cf[k];
+            }
+            const Clos cl = closure(par, ym, phi, km, cf, e);
+            if (!bnd) {
+                cm[k] = cl.C;
+                fm[k] = cl.K * (dy - 1.0);
+                unsat_interior = (k >= 1) && !(ym >= psi_sat);
+            } else {
+                const double q_inf_max = fmin(2.0 * (phi - cl.theta) * par[HB_P_DZ], cl.kb);
+                double p_left = 0.0;
+                if (ym < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(precip), q_inf_max);
+                if (mode == 1) p_left -= evaporation(par, ym);
+                HB_XA(c, NV, X_MISC)[0] = p_left;
+            }
         }
         const unsigned mask = __ballot_sync(HB_FULL, unsat_interior);
         if (mask) deepest = max(deepest, (warp << 5) + r * NT + (31 - __clz(mask)));
     }
-    int *wmax = reinterpret_cast<int *>(HB_X(c, X_WMAX));
+    int *wmax = reinterpret_cast<int *>(HB_XA(c, NV, X_WMAX));
     if (lane == 0) wmax[warp] = deepest;
-
-    // top boundary (bc_fun): closure at (y[0], z = x[0]) on the last thread,
-    // which has no midpoint in the last round
-    if (tid == NT - 1) {
-        const double y0 = y[0];
-        Clos b;
-        closure_cold(par, y0, par[HB_P_PHI_TOP], par[HB_P_KMEAN_TOP], par[HB_P_COEF_TOP], nr[0], &b);
-        const double q_inf_max = fmin(2.0 * (par[HB_P_PHI_TOP] - b.theta) * par[HB_P_DZ], b.kb);
-        double p_left = 0.0;
-        if (y0 < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(precip), q_inf_max);
-        if (mode == 1) {                 // daylight and not SPINUP
-            // np.all(theta_left > theta_res) over the broadcast profile (quirk Q2)
-            const double th_r = par[HB_P_THETA_RES];
-            const double ax = par[HB_P_ALPHA] * fabs(y0);
-            const double X = (par[HB_P_N] == 2.0) ? 1.0 / sqrt(1.0 + ax * ax)
-                                                   : pow(1.0 + pow(ax, par[HB_P_N]), -par[HB_P_M]);
-            const bool sat0 = y0 >= psi_sat;
-            const double dsm = sat0 ? par[HB_P_DSMIN_EXCL0] : par[HB_P_DSMIN_ALL];
-            if ((th_r + dsm * X > th_r) && (!sat0 || par[HB_P_PHI_TOP] > th_r))
-                p_left -= par[HB_P_SURF_EVAP];
-        }
-        HB_X(c, X_MISC)[0] = p_left;
-    }
     __syncthreads();
 
     // ---- phase B: lateral-flow sink (monitoring mode) and assembly ----------
@@ -300,43 +378,46 @@ __device__ __noinline__ void rhs_eval(const DevCtx &c, int col, double precip, i
         const int i = tid + r * NT;
         if (i < nx) {
             const double yi = y[i];
-            double s_i = 0.0, s_m = 0.0, res;
+            double s_i = 0.0, s_m = 0.0;
             if (i >= lo && i < hi) {          // own midpoint i
                 s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), 0.0);
                 lat += fabs(s_i);
             }
             if (i - 1 >= lo && i - 1 < hi)    // midpoint i-1
                 s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), 0.0);
+            // the three node types of richards_pde.py:109-156:
+            //   top     (p_left + (f_0 + zx*s_0)) / (zx*C_0)
+            //   inner   (f_i - f_{i-1} + (zx*s_i + xz*s_{i-1})) / (zx*C_i + xz*C_{i-1})
+            //   bottom  (0 + (f_{n-2} - xz*s_{n-2})) / (-xz*C_{n-2})
+            double num, den;
             if (i == 0) {
-                const double zx = c.zx[0];
-                double den = zx * cm[0];
-                if (den == 0.0) den = 1.0;
-                res = (HB_X(c, X_MISC)[0] + (fm[0] + zx * s_i)) / den;
+                const double zx = S.zx[0];
+                den = zx * cm[0];
+                num = HB_XA(c, NV, X_MISC)[0] + (fm[0] + zx * s_i);
             } else if (i < nx - 1) {
-                const double zx = c.zx[i], xz = c.xz[i];
-                double den = zx * cm[i] + xz * cm[i - 1];
-                if (den == 0.0) den = 1.0;
-                res = (fm[i] - fm[i - 1] + (zx * s_i + xz * s_m)) / den;
+                const double zx = S.zx[i], xz = S.xz[i];
+                den = zx * cm[i] + xz * cm[i - 1];
+                num = fm[i] - fm[i - 1] + (zx * s_i + xz * s_m);
             } else {
-                const double xz = c.xz[i];
-                double den = -xz * cm[i - 1];
-                if (den == 0.0) den = 1.0;
-                res = (0.0 + (fm[i - 1] - xz * s_m)) / den;
+                const double xz = S.xz[i];
+                den = -xz * cm[i - 1];
+                num = 0.0 + (fm[i - 1] - xz * s_m);
             }
-            fo[i] = res;
+            if (den == 0.0) den = 1.0;
+            fo[i] = hb_div(num, den);
         }
     }
     lat = warp_sum(lat);
-    if (lane == 0) HB_X(c, X_LATW)[warp] = lat;
+    if (lane == 0) HB_XA(c, NV, X_LATW)[warp] = lat;
 }
 
 // Lateral flow of the last RHS evaluation (arg_out, quirk Q6); thread 0 only.
-template <int NT>
+template <int NT, int NV>
 __device__ inline double lateral_flow(const DevCtx &c)
 {
     double lat = 0.0;
-    for (int w = 0; w < NT / 32; ++w) lat += HB_X(c, X_LATW)[w];
-    return lat * HB_X(c, X_PAR)[HB_P_DZ];
+    for (int w = 0; w < NT / 32; ++w) lat += HB_XA(c, NV, X_LATW)[w];
+    return lat * HB_XA(c, NV, X_PAR)[HB_P_DZ];
 }
 
 // ---------------------------------------------------------------------------
@@ -346,14 +427,32 @@ __device__ inline double lateral_flow(const DevCtx &c)
 // unknown, the others are eliminated locally (Thomas, no pivoting) and their
 // coupling to the two neighbouring interfaces is kept as spike vectors.  The 32
 // interface unknowns form a tridiagonal system solved by PCR with shuffles.
+// Loops are deliberately rolled: measured on B200, a fully unrolled,
+// register-resident variant (3x more SASS) made the whole kernel 20 % slower --
+// the instruction footprint of the hot loop matters more than the length of the
+// dependent chain.  (This solver is ours, not
+// a restatement of reference arithmetic, so FMA contraction and a
+// Newton-refined reciprocal are used.)
 // ---------------------------------------------------------------------------
+__device__ __noinline__ double fast_rcp(double x)
+{
+    const double ax = fabs(x);
+    if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+    double r = (double)__frcp_rn((float)x);
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+
+template <int NV>
 __device__ __noinline__ void tri_factor(const DevCtx &c, double cc)
 {
     const int lane = threadIdx.x & 31;
     const int nx = c.nx;
     const double *jl = HB_VEC(c, V_JL), *jd = HB_VEC(c, V_JD), *ju = HB_VEC(c, V_JU);
     double *tw = HB_VEC(c, V_TW), *tip = HB_VEC(c, V_TIP), *tvl = HB_VEC(c, V_TVL),
-           *tvr = HB_VEC(c, V_TVR), *pcr = HB_X(c, X_PCR);
+           *tvr = HB_VEC(c, V_TVR), *pcr = HB_XA(c, NV, X_PCR);
     const int m = (nx + 31) >> 5;
     const int s = lane * m;
     const int e = min(s + m, nx) - 1;           // inclusive; e < s: lane has no rows
@@ -361,31 +460,32 @@ __device__ __noinline__ void tri_factor(const DevCtx &c, double cc)
     double vl_last = 0.0, vr_last = 0.0, vl_first = 0.0, vr_first = 0.0;
     if (cnt >= 2) {
         // interior rows s..e-1
-        double piv = 1.0 - cc * jd[s];
-        double ip = 1.0 / piv;
+        double ip = fast_rcp(1.0 - cc * jd[s]);
         tw[s] = 0.0; tip[s] = ip;
         double g = -cc * jl[s];                 // rhs of the left spike, forward swept
         tvl[s] = g;
+#pragma unroll 1
         for (int r = s + 1; r < e; ++r) {
             const double w = (-cc * jl[r]) * ip;
-            piv = (1.0 - cc * jd[r]) - w * (-cc * ju[r - 1]);
-            ip = 1.0 / piv;
+            ip = fast_rcp(fma(-w, -cc * ju[r - 1], 1.0 - cc * jd[r]));
             tw[r] = w; tip[r] = ip;
             g = -w * g;
             tvl[r] = g;
         }
         // back substitution for both spikes
-        double zl = tvl[e - 1] * tip[e - 1];
-        double zr = (-cc * ju[e - 1]) * tip[e - 1];
+        double zl = tvl[e - 1] * ip;
+        double zr = (-cc * ju[e - 1]) * ip;
         tvl[e - 1] = zl; tvr[e - 1] = zr;
+        vl_last = zl; vr_last = zr;
+#pragma unroll 1
         for (int r = e - 2; r >= s; --r) {
-            const double cu = (-cc * ju[r]) * tip[r];
-            zl = tvl[r] * tip[r] - cu * zl;
+            const double ipr = tip[r];
+            const double cu = (-cc * ju[r]) * ipr;
+            zl = fma(-cu, zl, tvl[r] * ipr);
             zr = -cu * zr;
             tvl[r] = zl; tvr[r] = zr;
         }
-        vl_last = tvl[e - 1]; vr_last = tvr[e - 1];
-        vl_first = tvl[s]; vr_first = tvr[s];
+        vl_first = zl; vr_first = zr;
     }
     // interface row e
     double ae = 0.0, be = 1.0, ce = 0.0;
@@ -405,7 +505,7 @@ __device__ __noinline__ void tri_factor(const DevCtx &c, double cc)
     if (lane == 0) A = 0.0;
     pcr[11 * 32 + lane] = (cnt >= 2) ? ae : 0.0;             // multiplies z_last in rho
     pcr[12 * 32 + lane] = (has_n && cnt_n >= 2) ? ce : 0.0;  // multiplies z'_first in rho
-#pragma unroll
+#pragma unroll 1
     for (int st = 0; st < 5; ++st) {
         const int d = 1 << st;
         double Am = __shfl_up_sync(HB_FULL, A, d), Bm = __shfl_up_sync(HB_FULL, B, d),
@@ -414,24 +514,25 @@ __device__ __noinline__ void tri_factor(const DevCtx &c, double cc)
                Cp = __shfl_down_sync(HB_FULL, C, d);
         if (lane < d) { Am = 0.0; Bm = 1.0; Cm = 0.0; }
         if (lane + d > 31) { Ap = 0.0; Bp = 1.0; Cp = 0.0; }
-        const double k1 = A / Bm, k2 = C / Bp;
+        const double k1 = A * fast_rcp(Bm), k2 = C * fast_rcp(Bp);
         pcr[(2 * st) * 32 + lane] = k1;
         pcr[(2 * st + 1) * 32 + lane] = k2;
         B = B - k1 * Cm - k2 * Ap;
         A = -k1 * Am;
         C = -k2 * Cp;
     }
-    pcr[10 * 32 + lane] = 1.0 / B;
+    pcr[10 * 32 + lane] = fast_rcp(B);
     __syncwarp();
 }
 
 // Solves in place: V_B holds the rhs on entry, the solution on exit.
+template <int NV>
 __device__ __noinline__ void tri_solve(const DevCtx &c, double cc)
 {
     const int lane = threadIdx.x & 31;
     const int nx = c.nx;
     const double *ju = HB_VEC(c, V_JU), *tw = HB_VEC(c, V_TW), *tip = HB_VEC(c, V_TIP),
-                 *tvl = HB_VEC(c, V_TVL), *tvr = HB_VEC(c, V_TVR), *pcr = HB_X(c, X_PCR);
+                 *tvl = HB_VEC(c, V_TVL), *tvr = HB_VEC(c, V_TVR), *pcr = HB_XA(c, NV, X_PCR);
     double *b = HB_VEC(c, V_B);
     const int m = (nx + 31) >> 5;
     const int s = lane * m;
@@ -439,52 +540,67 @@ __device__ __noinline__ void tri_solve(const DevCtx &c, double cc)
     const int cnt = e - s + 1;
     double z_first = 0.0, z_last = 0.0;
     if (cnt >= 2) {
+        // forward sweep; the operands of the next row are fetched before the
+        // dependent FMA of the current one
         double g = b[s];
-        for (int r = s + 1; r < e; ++r) {       // forward sweep
-            g = fma(-tw[r], g, b[r]);
+        int rn = (s + 1 < e) ? s + 1 : s;
+        double wn = tw[rn], bn = b[rn];
+#pragma unroll 1
+        for (int r = s + 1; r < e; ++r) {
+            const double w = wn, br = bn;
+            rn = (r + 1 < e) ? r + 1 : r;
+            wn = tw[rn]; bn = b[rn];
+            g = fma(-w, g, br);
             b[r] = g;
         }
         double z = g * tip[e - 1];
         b[e - 1] = z;
-        for (int r = e - 2; r >= s; --r) {      // backward sweep
-            const double ip = tip[r];
-            const double cu = (-cc * ju[r]) * ip;
-            z = fma(-cu, z, b[r] * ip);
+        z_last = z;
+        // backward sweep
+        int rq = (e - 2 >= s) ? e - 2 : s;
+        double ipn = tip[rq], jun = ju[rq], bq = b[rq];
+#pragma unroll 1
+        for (int r = e - 2; r >= s; --r) {
+            const double cu = (-cc * jun) * ipn, t0 = bq * ipn;
+            rq = (r - 1 >= s) ? r - 1 : s;
+            ipn = tip[rq]; jun = ju[rq]; bq = b[rq];
+            z = fma(-cu, z, t0);
             b[r] = z;
         }
-        z_first = z; z_last = b[e - 1];
+        z_first = z;
     }
     double rho = (cnt >= 1) ? b[e] : 0.0;
     const double zf_n = __shfl_down_sync(HB_FULL, z_first, 1);
     rho -= pcr[11 * 32 + lane] * z_last;
     rho -= pcr[12 * 32 + lane] * ((lane < 31) ? zf_n : 0.0);
-#pragma unroll
+#pragma unroll 1
     for (int st = 0; st < 5; ++st) {
         const int d = 1 << st;
         double rm = __shfl_up_sync(HB_FULL, rho, d);
         double rp = __shfl_down_sync(HB_FULL, rho, d);
         if (lane < d) rm = 0.0;
         if (lane + d > 31) rp = 0.0;
-        rho = rho - pcr[(2 * st) * 32 + lane] * rm - pcr[(2 * st + 1) * 32 + lane] * rp;
+        rho = fma(-pcr[(2 * st + 1) * 32 + lane], rp, fma(-pcr[(2 * st) * 32 + lane], rm, rho));
     }
     const double xi = rho * pcr[10 * 32 + lane];
     double x_left = __shfl_up_sync(HB_FULL, xi, 1);
     if (lane == 0) x_left = 0.0;
     if (cnt >= 1) b[e] = xi;
+#pragma unroll 1
     for (int r = s; r < e; ++r)
-        b[r] = b[r] - x_left * tvl[r] - xi * tvr[r];
+        b[r] = fma(-xi, tvr[r], fma(-x_left, tvl[r], b[r]));
     __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
 // change_D (SCIPY bdf.py:18-33): D[0..order] <- (R U)^T D[0..order].
 // ---------------------------------------------------------------------------
-template <int NT>
+template <int NT, int NV>
 __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
 {
     const int tid = threadIdx.x;
     const int q = order + 1;
-    double *ru = HB_X(c, X_RU);
+    double *ru = HB_XA(c, NV, X_RU);
     __syncthreads();                       // previous readers of RU are done
     if (tid < q * q) {
         const int i = tid / q, j = tid % q;
@@ -519,221 +635,346 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
     }
 }
 
-// ---------------------------------------------------------------------------
-// Forward-difference Jacobian on the tridiagonal pattern with scipy's column
-// grouping and step-factor adaptation (SCIPY common.py:268-341,385-455).
-// The evaluation point is taken from vector `src` (V_D: D[0] at window start;
-// V_B: the predictor).  Uses V_TW (f at the base point), V_TIP (f at the
-// perturbed point), V_TVL (copy of the base point), V_TVR (steps h) -- the
-// tridiagonal factors are invalid after a Jacobian refresh anyway -- and V_Y as
-// the RHS input.  Result: row storage in V_JL / V_JD / V_JU, factors in V_FAC.
-// ---------------------------------------------------------------------------
-template <int NT, int CPT>
-__device__ __noinline__ void num_jac(const DevCtx &c, int col, double precip, int wtd, int mode,
-                                     int src, bool first, Counters &cnt)
+// Column statistics of the grouped forward differences with scipy's
+// sparse-argmax semantics (common.py:391-396, sparse/_data.py:249-275): first
+// maximum among the stored rows j-1..j+1, row 0 when the column is all zero.
+struct ColStat { double dl, dd, du, maxd, scl; };
+
+__device__ __noinline__ void column_stats(const double *fb, const double *fn, int j, int nx,
+                                          ColStat *o)
 {
-    const int nx = c.nx, tid = threadIdx.x;
-    double *y = HB_VEC(c, V_Y), *fb = HB_VEC(c, V_TW), *fn = HB_VEC(c, V_TIP),
-           *yb = HB_VEC(c, V_TVL), *hv = HB_VEC(c, V_TVR), *fac = HB_VEC(c, V_FAC);
-    const double *ysrc = HB_VEC(c, src);
-    double ysc[CPT], cl[CPT], cd[CPT], cu[CPT], maxd[CPT], scl[CPT];
-    bool small_[CPT];
-
-    __syncthreads();
-    for (int i = tid; i < nx; i += NT) { const double v = ysrc[i]; yb[i] = v; y[i] = v; }
-    __syncthreads();
-    rhs_eval<NT, CPT>(c, col, precip, wtd, mode, V_TW); cnt.nrhs++;   // jac_wrapped: f = fun_single(t, y)
-#pragma unroll
-    for (int r = 0; r < CPT; ++r) {
-        const int i = tid + r * NT;
-        ysc[r] = 0.0; cl[r] = cd[r] = cu[r] = 0.0; maxd[r] = 0.0; scl[r] = 0.0;
-        small_[r] = false;
-        if (i < nx) {
-            double fc = first ? sqrt(HB_EPS) : fac[i];
-            const double fs = (fb[i] >= 0.0) ? 1.0 : -1.0;
-            const double ybi = yb[i];
-            ysc[r] = fs * fmax(c.atol, fabs(ybi));
-            double h = (ybi + fc * ysc[r]) - ybi;
-            while (h == 0.0) { fc *= 10.0; h = (ybi + fc * ysc[r]) - ybi; }
-            fac[i] = fc; hv[i] = h;
-        }
+    const int lo = j > 0 ? j - 1 : 0, hi = j < nx - 1 ? j + 1 : nx - 1;
+    int best = lo; double bv = fabs(fn[lo] - fb[lo]);
+    for (int i = lo + 1; i <= hi; ++i) {
+        const double v = fabs(fn[i] - fb[i]);
+        if (v > bv) { bv = v; best = i; }
     }
-    const double REJECT = pow(HB_EPS, 0.875), SMALL = pow(HB_EPS, 0.75), BIG = pow(HB_EPS, 0.25);
-
-    // column statistics with scipy's sparse-argmax semantics (_data.py:249-275)
-    auto column_stats = [&](int j, double &dl_, double &dd_, double &du_, double &md, double &sc) {
-        const int lo = j > 0 ? j - 1 : 0, hi = j < nx - 1 ? j + 1 : nx - 1;
-        int best = lo; double bv = fabs(fn[lo] - fb[lo]);
-        for (int i = lo + 1; i <= hi; ++i) {
-            const double v = fabs(fn[i] - fb[i]);
-            if (v > bv) { bv = v; best = i; }
-        }
-        int mi;
-        if (bv > 0.0) { mi = best; md = bv; }
-        else { mi = 0; md = (lo == 0) ? fabs(fn[0] - fb[0]) : 0.0; }
-        sc = fmax(fabs(fb[mi]), fabs(fn[mi]));
-        dl_ = (j > 0) ? fn[j - 1] - fb[j - 1] : 0.0;
-        dd_ = fn[j] - fb[j];
-        du_ = (j < nx - 1) ? fn[j + 1] - fb[j + 1] : 0.0;
-    };
-
-    for (int g = 0; g < c.ng; ++g) {
-        for (int i = tid; i < nx; i += NT) y[i] = yb[i] + ((c.grp[i] == g) ? hv[i] : 0.0);
-        __syncthreads();
-        rhs_eval<NT, CPT>(c, col, precip, wtd, mode, V_TIP); cnt.nrhs++;
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) {
-            const int j = tid + r * NT;
-            if (j < nx && c.grp[j] == g) {
-                column_stats(j, cl[r], cd[r], cu[r], maxd[r], scl[r]);
-                small_[r] = maxd[r] < REJECT * scl[r];
-            }
-        }
-    }
-    bool any_small = false;
-#pragma unroll
-    for (int r = 0; r < CPT; ++r) any_small |= small_[r];
-    if (__syncthreads_or(any_small)) {
-        double hn[CPT];
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) {
-            const int i = tid + r * NT;
-            hn[r] = 0.0;
-            if (i < nx && small_[r]) hn[r] = (yb[i] + 10.0 * fac[i] * ysc[r]) - yb[i];
-        }
-        for (int g = 0; g < c.ng; ++g) {
-            bool mine = false;
-#pragma unroll
-            for (int r = 0; r < CPT; ++r) {
-                const int i = tid + r * NT;
-                mine |= (i < nx) && small_[r] && (c.grp[i] == g);
-            }
-            if (!__syncthreads_or(mine)) continue;
-#pragma unroll
-            for (int r = 0; r < CPT; ++r) {
-                const int i = tid + r * NT;
-                if (i < nx) y[i] = yb[i] + ((c.grp[i] == g) ? hn[r] : 0.0);
-            }
-            __syncthreads();
-            rhs_eval<NT, CPT>(c, col, precip, wtd, mode, V_TIP); cnt.nrhs++;
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < CPT; ++r) {
-                const int j = tid + r * NT;
-                if (j < nx && small_[r] && c.grp[j] == g) {
-                    double nl, nd, nu, md, sn;
-                    column_stats(j, nl, nd, nu, md, sn);
-                    if (maxd[r] * sn < md * scl[r]) {
-                        fac[j] = 10.0 * fac[j];
-                        hv[j] = hn[r];
-                        cl[r] = nl; cd[r] = nd; cu[r] = nu;
-                        scl[r] = sn; maxd[r] = md;
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();                       // all reads of fb / fn are done
-    // column storage: cl = J[j-1][j], cd = J[j][j], cu = J[j+1][j]
-    double *jl = HB_VEC(c, V_JL), *jd = HB_VEC(c, V_JD), *ju = HB_VEC(c, V_JU);
-#pragma unroll
-    for (int r = 0; r < CPT; ++r) {
-        const int j = tid + r * NT;
-        if (j < nx) {
-            const double h = hv[j];
-            fb[j] = cl[r] / h;             // upper entry of row j-1
-            jd[j] = cd[r] / h;
-            fn[j] = cu[r] / h;             // lower entry of row j+1
-            double fc = fac[j];
-            if (maxd[r] < SMALL * scl[r]) fc *= 10.0;
-            if (maxd[r] > BIG * scl[r]) fc *= 0.1;
-            fac[j] = fmax(fc, 1e3 * HB_EPS);
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < nx; i += NT) {
-        jl[i] = (i > 0) ? fn[i - 1] : 0.0;
-        ju[i] = (i < nx - 1) ? fb[i + 1] : 0.0;
-    }
-    __syncthreads();
-    cnt.njev++;
+    int mi;
+    if (bv > 0.0) { mi = best; o->maxd = bv; }
+    else { mi = 0; o->maxd = (lo == 0) ? fabs(fn[0] - fb[0]) : 0.0; }
+    o->scl = fmax(fabs(fb[mi]), fabs(fn[mi]));
+    o->dl = (j > 0) ? fn[j - 1] - fb[j - 1] : 0.0;
+    o->dd = fn[j] - fb[j];
+    o->du = (j < nx - 1) ? fn[j + 1] - fb[j + 1] : 0.0;
 }
 
 // ---------------------------------------------------------------------------
-// One solve_ivp(method='BDF') call from t0 to t_bound.  y0 is read from
-// global memory (y_glob); on exit V_Y holds solver.y, the last accepted state
+// One solve_ivp(method='BDF') call from t0 to t_bound, as a state machine
+// around a single right-hand-side evaluation.  y0 is read from global memory
+// (y_glob); on exit V_Y holds solver.y, the last accepted state
 // (ivp.py:659-666).  Returns 0 (finished) or -1 (step size underflow).
+//
+// Jacobian scratch while a forward-difference Jacobian is being built (the
+// tridiagonal factors and the Newton vectors are dead then):
+//   V_TW  f at the base point        V_TIP f at the perturbed point
+//   V_TVL the base point             V_TVR step h
+//   V_JL/V_JD/V_JU un-normalised column differences J[j-1][j], J[j][j], J[j+1][j]
+//   V_PSI max |difference|           V_SCL its scale       V_DD "too small" flag
 // ---------------------------------------------------------------------------
-template <int NT, int CPT>
+template <int NT, int CPT, bool FULL>
 __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip, int wtd, int mode,
                                         double t0, double t_bound, const double *y_glob,
-                                        Counters &cnt)
+                                        int jac_only = 0)
 {
+    // jac_only (test hook): 1 = return after the initial Jacobian, 2 = the same
+    // but starting from the step factors already in V_FAC.
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
+    enum { S_F0, S_F1, S_JB, S_JG, S_JR, S_NW };
+    enum { GO_NONE, GO_JAC_END, GO_STEP_BEGIN, GO_STEP_RETRY, GO_PREDICT, GO_NEWTON_BEGIN,
+           GO_JAC_BEGIN };
     const int nx = c.nx, nxp = c.nxp, tid = threadIdx.x;
     const double rtol = c.rtol, atol = c.atol;
     const double newton_tol = fmax(10.0 * HB_EPS / rtol, fmin(0.03, sqrt(rtol)));
     double *D = HB_VEC(c, V_D), *y = HB_VEC(c, V_Y), *b = HB_VEC(c, V_B);
-    double d_[CPT], psi_[CPT], scl_[CPT];
-    int par_ = 0;                               // block-reduction slot parity
+    double *vpsi = HB_VEC(c, V_PSI), *vscl = HB_VEC(c, V_SCL), *vd = HB_VEC(c, V_DD);
+    double *fbv = HB_VEC(c, V_TW), *fnv = HB_VEC(c, V_TIP), *ybv = HB_VEC(c, V_TVL),
+           *hv = HB_VEC(c, V_TVR), *fac = HB_VEC(c, V_FAC);
+    double *jl = HB_VEC(c, V_JL), *jd = HB_VEC(c, V_JD), *ju = HB_VEC(c, V_JU);
+    long long *cnt = reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT));
+    const Statics S = statics_of<FULL>(c, col);
+    int par_ = 0;                                   // block-reduction slot parity
 
-    // ---- BDF.__init__ (bdf.py:198-256) ---------------------------------------
+    // controller state (identical in every thread)
+    int state = S_F0, order = 1, n_equal = 0, k_newton = 0, jac_g = 0;
+    bool lu_valid = false, current_jac = false, have_old = false, jac_first = true, jac_init = true;
+    double t = t0, t_new = t0, h_abs = 0.0, h_loc = 0.0, min_step = 0.0, cc = 0.0, c_lu = 0.0;
+    double dy_norm_old = 0.0, d1_init = 0.0, h0_init = 0.0;
+
     __syncthreads();
     for (int i = tid; i < nx; i += NT) { const double v = y_glob[i]; y[i] = v; D[i] = v; }
-    __syncthreads();
-    rhs_eval<NT, CPT>(c, col, precip, wtd, mode, V_D + 1); cnt.nrhs++; cnt.nfev++;   // f0 -> D[1]
-    double h_abs;
-    {   // select_initial_step (common.py:68-134), order 1
-        const double interval = fabs(t_bound - t0);
-        double l0 = 0.0, l1 = 0.0;
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) {
-            const int i = tid + r * NT;
-            scl_[r] = 1.0;
-            if (i < nx) {
+
+    for (;;) {
+        // ======== the single right-hand-side evaluation ========================
+        const int out = (state == S_F0) ? V_D + 1 : (state == S_JB) ? V_TW
+                      : (state == S_JG || state == S_JR) ? V_TIP : V_B;
+        __syncthreads();
+        rhs_eval<NT, CPT, NV>(c, S, precip, wtd, mode, out);
+        if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
+        int go = GO_NONE;
+
+        if (state == S_NW) {
+            // ---- one Newton iteration (solve_bdf_system, bdf.py:41-67) --------
+            bool finite = true;
+            for (int i = tid; i < nx; i += NT) {
+                const double f = b[i];
+                finite &= isfinite(f);
+                b[i] = cc * f - vpsi[i] - vd[i];
+            }
+            bool converged = false, stop = false;
+            if (!__syncthreads_and(finite)) stop = true;
+            else {
+                if (tid < 32) tri_solve<NV>(c, c_lu);
+                if (tid == 0) cnt[K_NNEWTON]++;
+                __syncthreads();
+                double loc = 0.0;
+                for (int i = tid; i < nx; i += NT) {
+                    const double dy = b[i];
+                    const double q = hb_div(dy, vscl[i]);
+                    loc += q * q;
+                    y[i] += dy;                    // tentative: discarded if we stop
+                    vd[i] += dy;
+                }
+                const double dy_norm = rms<NT, NV>(c, par_, loc);
+                double rate = 0.0;
+                if (have_old) {
+                    rate = hb_div(dy_norm, dy_norm_old);
+                    if (rate >= 1.0 ||
+                        hb_div(ipow(rate, HB_NEWTON_MAXITER - k_newton), 1.0 - rate) * dy_norm > newton_tol)
+                        stop = true;
+                }
+                if (!stop && (dy_norm == 0.0 ||
+                              (have_old && hb_div(rate, 1.0 - rate) * dy_norm < newton_tol))) {
+                    converged = true; stop = true;
+                }
+                dy_norm_old = dy_norm; have_old = true;
+            }
+            const int n_iter = k_newton + 1;
+            k_newton++;
+            if (!stop && k_newton < HB_NEWTON_MAXITER) continue;      // next Newton iteration
+            if (!converged) {
+                if (!current_jac) {
+                    // refresh the Jacobian at (t_new, y_predict) and try again (bdf.py:375-380)
+                    __syncthreads();
+                    for (int i = tid; i < nx; i += NT) {
+                        double acc = D[i];
+                        for (int kk = 1; kk <= order; ++kk) acc += D[kk * nxp + i];
+                        b[i] = acc;
+                    }
+                    jac_first = false; jac_init = false;
+                    go = GO_JAC_BEGIN;
+                } else {
+                    h_loc *= 0.5;
+                    change_D<NT, NV>(c, order, 0.5);
+                    n_equal = 0; lu_valid = false;
+                    if (tid == 0) cnt[K_NREJECT]++;
+                    go = GO_STEP_RETRY;
+                }
+            } else {
+                // ---- error test (bdf.py:390-406) ------------------------------
+                const double safety = 0.9 * (2 * HB_NEWTON_MAXITER + 1) /
+                                      (double)(2 * HB_NEWTON_MAXITER + n_iter);
+                double le = 0.0;
+                for (int i = tid; i < nx; i += NT) {
+                    const double sc = atol + rtol * fabs(y[i]);
+                    vscl[i] = sc;
+                    const double q = hb_div(k_error_const[order] * vd[i], sc);
+                    le += q * q;
+                }
+                const double error_norm = rms<NT, NV>(c, par_, le);
+                if (error_norm > 1.0) {
+                    const double factor = fmax(HB_MIN_FACTOR, safety * inv_root(error_norm, order + 1));
+                    h_loc *= factor;
+                    change_D<NT, NV>(c, order, factor);
+                    n_equal = 0;
+                    if (tid == 0) cnt[K_NREJECT]++;
+                    go = GO_STEP_RETRY;
+                } else {
+                    // ---- accepted: update differences (bdf.py:408-424) --------
+                    n_equal++;
+                    t = t_new;
+                    h_abs = h_loc;
+                    if (tid == 0) cnt[K_NSTEPS]++;
+                    const bool decide = (n_equal >= order + 1);
+                    double lm = 0.0, lp = 0.0;
+                    for (int i = tid; i < nx; i += NT) {
+                        const double di = vd[i];
+                        D[(order + 2) * nxp + i] = di - D[(order + 1) * nxp + i];
+                        D[(order + 1) * nxp + i] = di;
+                        for (int kk = order; kk >= 0; --kk) D[kk * nxp + i] += D[(kk + 1) * nxp + i];
+                        if (decide) {
+                            const double sc = vscl[i];
+                            if (order > 1) {
+                                const double q = hb_div(k_error_const[order - 1] * D[order * nxp + i], sc);
+                                lm += q * q;
+                            }
+                            if (order < HB_MAX_ORDER) {
+                                const double q = hb_div(k_error_const[order + 1] * D[(order + 2) * nxp + i], sc);
+                                lp += q * q;
+                            }
+                        }
+                    }
+                    if (decide) {
+                        // ---- order / step selection (bdf.py:426-453) ----------
+                        double em = INFINITY, ep = INFINITY;
+                        if (order > 1) em = rms<NT, NV>(c, par_, lm);
+                        if (order < HB_MAX_ORDER) ep = rms<NT, NV>(c, par_, lp);
+                        const double fm_ = inv_root(em, order), fe_ = inv_root(error_norm, order + 1),
+                                     fp_ = inv_root(ep, order + 2);
+                        int delta = -1; double best = fm_;
+                        if (fe_ > best) { best = fe_; delta = 0; }
+                        if (fp_ > best) { best = fp_; delta = 1; }
+                        order += delta;
+                        const double factor = fmin(HB_MAX_FACTOR, safety * best);
+                        h_abs *= factor;
+                        change_D<NT, NV>(c, order, factor);
+                        n_equal = 0; lu_valid = false;
+                    }
+                    go = GO_STEP_BEGIN;
+                }
+            }
+        } else if (state == S_F0) {
+            // ---- select_initial_step, first half (common.py:105-115) ----------
+            double l0 = 0.0, l1 = 0.0;
+            for (int i = tid; i < nx; i += NT) {
                 const double y0 = D[i];
-                scl_[r] = atol + fabs(y0) * rtol;
-                const double q0 = y0 / scl_[r], q1 = D[nxp + i] / scl_[r];
+                const double sc = atol + fabs(y0) * rtol;
+                vscl[i] = sc;
+                const double q0 = y0 / sc, q1 = D[nxp + i] / sc;
                 l0 += q0 * q0; l1 += q1 * q1;
             }
+            const double d0 = rms<NT, NV>(c, par_, l0);
+            d1_init = rms<NT, NV>(c, par_, l1);
+            const double h0 = (d0 < 1e-5 || d1_init < 1e-5) ? 1e-6 : 0.01 * d0 / d1_init;
+            h0_init = fmin(h0, fabs(t_bound - t0));
+            for (int i = tid; i < nx; i += NT) y[i] = D[i] + h0_init * D[nxp + i];
+            state = S_F1;
+        } else if (state == S_F1) {
+            // ---- select_initial_step, second half (common.py:116-134) ---------
+            double l2 = 0.0;
+            for (int i = tid; i < nx; i += NT) { const double q2 = (b[i] - D[nxp + i]) / vscl[i]; l2 += q2 * q2; }
+            const double d2 = rms<NT, NV>(c, par_, l2) / h0_init;
+            const double h1 = (d1_init <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0_init * 1e-3)
+                                                                 : sqrt(0.01 / fmax(d1_init, d2));
+            h_abs = fmin(fmin(100.0 * h0_init, h1), fabs(t_bound - t0));
+            for (int i = tid; i < nx; i += NT) b[i] = D[i];          // Jacobian at (t0, y0)
+            jac_first = (jac_only != 2); jac_init = true;
+            go = GO_JAC_BEGIN;
+        } else if (state == S_JB) {
+            // ---- num_jac: steps from the base value (common.py:320-341) -------
+            for (int i = tid; i < nx; i += NT) {
+                double fc = jac_first ? sqrt(HB_EPS) : fac[i];
+                const double ybi = ybv[i];
+                const double ysc = ((fbv[i] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
+                double h = (ybi + fc * ysc) - ybi;
+                while (h == 0.0) { fc *= 10.0; h = (ybi + fc * ysc) - ybi; }
+                fac[i] = fc; hv[i] = h;
+                vd[i] = 0.0;
+                y[i] = ybi + ((c.grp[i] == 0) ? h : 0.0);
+            }
+            jac_g = 0;
+            state = S_JG;
+        } else {
+            // ---- num_jac: differences of group jac_g (common.py:385-443) ------
+            const double REJECT = 2.0097183471152322e-14;     // EPS ** 0.875
+            __syncthreads();
+            for (int j = tid; j < nx; j += NT) {
+                if (c.grp[j] != jac_g) continue;
+                if (state == S_JG) {
+                    ColStat cs;
+                    column_stats(fbv, fnv, j, nx, &cs);
+                    jl[j] = cs.dl; jd[j] = cs.dd; ju[j] = cs.du;
+                    vpsi[j] = cs.maxd; vscl[j] = cs.scl;
+                    vd[j] = (cs.maxd < REJECT * cs.scl) ? 1.0 : 0.0;
+                } else if (vd[j] != 0.0) {
+                    ColStat cs;
+                    column_stats(fbv, fnv, j, nx, &cs);
+                    if (vpsi[j] * cs.scl < cs.maxd * vscl[j]) {
+                        fac[j] = 10.0 * fac[j];
+                        const double ybi = ybv[j];
+                        const double ysc = ((fbv[j] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
+                        hv[j] = (ybi + fac[j] * ysc) - ybi;
+                        jl[j] = cs.dl; jd[j] = cs.dd; ju[j] = cs.du;
+                        vscl[j] = cs.scl; vpsi[j] = cs.maxd;
+                    }
+                    vd[j] = 0.0;                   // handled
+                }
+            }
+            // next evaluation: remaining first-pass groups, then the groups that
+            // hold a column whose difference was too small (retry, 10x step)
+            int next_state = state, next_g = jac_g + 1;
+            bool done = false;
+            if (state == S_JG && next_g >= c.ng) { next_state = S_JR; next_g = 0; }
+            if (next_state == S_JR) {
+                int want = c.ng;
+                for (int j = tid; j < nx; j += NT)
+                    if (vd[j] != 0.0 && c.grp[j] >= next_g) want = min(want, c.grp[j]);
+                want = -block_max_int<NT, NV>(c, par_, -want);
+                if (want >= c.ng) done = true; else next_g = want;
+            }
+            if (done) go = GO_JAC_END;
+            else {
+                for (int i = tid; i < nx; i += NT) {
+                    double step = 0.0;
+                    if (c.grp[i] == next_g) {
+                        if (next_state == S_JG) step = hv[i];
+                        else if (vd[i] != 0.0) {
+                            const double ybi = ybv[i];
+                            const double ysc = ((fbv[i] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
+                            step = (ybi + 10.0 * fac[i] * ysc) - ybi;
+                        }
+                    }
+                    y[i] = ybv[i] + step;
+                }
+                jac_g = next_g; state = next_state;
+            }
         }
-        const double d0 = rms<NT>(c, par_, l0), d1 = rms<NT>(c, par_, l1);
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h0 = fmin(h0, interval);
-        for (int i = tid; i < nx; i += NT) y[i] = D[i] + h0 * D[nxp + i];
-        __syncthreads();
-        rhs_eval<NT, CPT>(c, col, precip, wtd, mode, V_B); cnt.nrhs++; cnt.nfev++;
-        double l2 = 0.0;
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) {
-            const int i = tid + r * NT;
-            if (i < nx) { const double q2 = (b[i] - D[nxp + i]) / scl_[r]; l2 += q2 * q2; }
-        }
-        const double d2 = rms<NT>(c, par_, l2) / h0;
-        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
-                                                       : sqrt(0.01 / fmax(d1, d2));
-        h_abs = fmin(fmin(100.0 * h0, h1), interval);
-    }
-    num_jac<NT, CPT>(c, col, precip, wtd, mode, V_D, true, cnt);
-    for (int i = tid; i < nx; i += NT) D[nxp + i] = D[nxp + i] * h_abs;
-    int order = 1, n_equal = 0;
-    bool lu_valid = false;
-    double t = t0;
-    double c_lu = 0.0;
 
-    // ---- driver loop (ivp.py:659, base.py:159-197) ----------------------------
-    while (t != t_bound) {
-        const double min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
-        double h_loc;
-        if (h_abs < min_step) {
-            h_loc = min_step;
-            change_D<NT>(c, order, min_step / h_abs);
-            n_equal = 0;
-        } else h_loc = h_abs;
-        bool current_jac = false, accepted = false;
-        int n_iter = 0;
-        double t_new = t, safety = 0.0, error_norm = 0.0;
-        while (!accepted) {
+        if (go == GO_JAC_END) {
+            // ---- num_jac: normalise, adapt factors, column -> row storage ------
+            const double SMALL = 1.8189894035458565e-12;      // EPS ** 0.75
+            const double BIG = 1.220703125e-04;               // EPS ** 0.25
+            __syncthreads();
+            for (int j = tid; j < nx; j += NT) {
+                const double h = hv[j];
+                fbv[j] = hb_div(jl[j], h);     // J[j-1][j]: upper entry of row j-1
+                jd[j] = hb_div(jd[j], h);
+                fnv[j] = hb_div(ju[j], h);     // J[j+1][j]: lower entry of row j+1
+                double fc = fac[j];
+                if (vpsi[j] < SMALL * vscl[j]) fc *= 10.0;
+                if (vpsi[j] > BIG * vscl[j]) fc *= 0.1;
+                fac[j] = fmax(fc, 1e3 * HB_EPS);
+            }
+            __syncthreads();
+            for (int i = tid; i < nx; i += NT) {
+                jl[i] = (i > 0) ? fnv[i - 1] : 0.0;
+                ju[i] = (i < nx - 1) ? fbv[i + 1] : 0.0;
+            }
+            if (tid == 0) cnt[K_NJEV]++;
+            lu_valid = false;
+            if (jac_init) {
+                if (jac_only) { __syncthreads(); return 0; }
+                for (int i = tid; i < nx; i += NT) D[nxp + i] = D[nxp + i] * h_abs;   // D[1] = f0 * h
+                order = 1; n_equal = 0; t = t0;
+                go = GO_STEP_BEGIN;
+            } else {
+                current_jac = true;
+                go = GO_PREDICT;               // same t_new, h: rebuild predictor, psi, scale
+            }
+        }
+        if (go == GO_STEP_BEGIN) {
+            // ---- driver loop / top of _step_impl (ivp.py:659, bdf.py:318-333) --
+            if (t == t_bound) { __syncthreads(); return 0; }
+            min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
+            if (h_abs < min_step) {
+                h_loc = min_step;
+                change_D<NT, NV>(c, order, min_step / h_abs);
+                n_equal = 0;
+            } else h_loc = h_abs;
+            current_jac = false;
+            go = GO_STEP_RETRY;
+        }
+        if (go == GO_STEP_RETRY) {
+            // ---- top of the `while not step_accepted` loop (bdf.py:345-358) ---
             if (h_loc < min_step) {
                 // failure: solver.y is the last accepted state == D[0]
                 __syncthreads();
@@ -741,199 +982,81 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 __syncthreads();
                 return -1;
             }
-            double h = h_loc;
-            t_new = t + h;
+            t_new = t + h_loc;
             if (t_new - t_bound > 0.0) {
                 t_new = t_bound;
-                change_D<NT>(c, order, fabs(t_new - t) / h_loc);
+                change_D<NT, NV>(c, order, fabs(t_new - t) / h_loc);
                 n_equal = 0; lu_valid = false;
             }
-            h = t_new - t; h_loc = fabs(h);
-            // predictor, scale and psi (bdf.py:360-363); predictor kept in V_B
+            h_loc = fabs(t_new - t);
+            go = GO_PREDICT;
+        }
+        if (go == GO_PREDICT) {
+            // ---- predictor, scale, psi (bdf.py:360-366) ----------------------
+            cc = hb_div(t_new - t, k_alpha[order]);
             __syncthreads();
-#pragma unroll
-            for (int r = 0; r < CPT; ++r) {
-                const int i = tid + r * NT;
-                psi_[r] = 0.0; scl_[r] = 1.0;
-                if (i < nx) {
-                    double acc = D[i], ps = 0.0;
-                    for (int k = 1; k <= order; ++k) {
-                        const double dk = D[k * nxp + i];
-                        acc += dk; ps += dk * k_gamma[k];
-                    }
-                    scl_[r] = atol + rtol * fabs(acc);
-                    psi_[r] = ps / k_alpha[order];
-                    y[i] = acc;
+            for (int i = tid; i < nx; i += NT) {
+                double acc = D[i], ps = 0.0;
+                for (int kk = 1; kk <= order; ++kk) {
+                    const double dk = D[kk * nxp + i];
+                    acc += dk; ps += dk * k_gamma[kk];
                 }
+                y[i] = acc;
+                vscl[i] = atol + rtol * fabs(acc);
+                vpsi[i] = hb_div(ps, k_alpha[order]);
+                vd[i] = 0.0;
             }
-            bool converged = false;
-            const double cc = h / k_alpha[order];
-            while (!converged) {
-                if (!lu_valid) {
-                    __syncthreads();
-                    if (tid < 32) tri_factor(c, cc);
-                    c_lu = cc; lu_valid = true; cnt.nlu++;
-                }
-                // solve_bdf_system (bdf.py:36-69); V_Y holds y_predict
-#pragma unroll
-                for (int r = 0; r < CPT; ++r) d_[r] = 0.0;
+            go = GO_NEWTON_BEGIN;
+        }
+        if (go == GO_NEWTON_BEGIN) {
+            if (!lu_valid) {
                 __syncthreads();
-                double dy_norm_old = 0.0; bool have_old = false; int k;
-                for (k = 0; k < HB_NEWTON_MAXITER; ++k) {
-                    rhs_eval<NT, CPT>(c, col, precip, wtd, mode, V_B); cnt.nrhs++; cnt.nfev++;
-                    bool finite = true;
-#pragma unroll
-                    for (int r = 0; r < CPT; ++r) {
-                        const int i = tid + r * NT;
-                        if (i < nx) {
-                            const double f = b[i];
-                            finite &= isfinite(f);
-                            b[i] = cc * f - psi_[r] - d_[r];
-                        }
-                    }
-                    if (!__syncthreads_and(finite)) break;
-                    if (tid < 32) tri_solve(c, c_lu);
-                    cnt.nnewton++;
-                    __syncthreads();
-                    double loc = 0.0;
-#pragma unroll
-                    for (int r = 0; r < CPT; ++r) {
-                        const int i = tid + r * NT;
-                        if (i < nx) {
-                            const double dy = b[i];
-                            const double q = dy / scl_[r];
-                            loc += q * q;
-                            y[i] += dy;            // tentative: discarded if we break
-                            d_[r] += dy;
-                        }
-                    }
-                    const double dy_norm = rms<NT>(c, par_, loc);
-                    double rate = 0.0;
-                    if (have_old) {
-                        rate = dy_norm / dy_norm_old;
-                        if (rate >= 1.0 ||
-                            ipow(rate, HB_NEWTON_MAXITER - k) / (1.0 - rate) * dy_norm > newton_tol)
-                            break;
-                    }
-                    if (dy_norm == 0.0 || (have_old && rate / (1.0 - rate) * dy_norm < newton_tol)) {
-                        converged = true; break;
-                    }
-                    dy_norm_old = dy_norm; have_old = true;
-                }
-                n_iter = (k < HB_NEWTON_MAXITER) ? k + 1 : HB_NEWTON_MAXITER;
-                if (!converged) {
-                    // rebuild the predictor (V_Y was advanced tentatively)
-                    __syncthreads();
-                    for (int i = tid; i < nx; i += NT) {
-                        double acc = D[i];
-                        for (int kk = 1; kk <= order; ++kk) acc += D[kk * nxp + i];
-                        y[i] = acc; b[i] = acc;
-                    }
-                    if (current_jac) break;
-                    num_jac<NT, CPT>(c, col, precip, wtd, mode, V_B, false, cnt);
-                    // num_jac used V_Y as its work vector: restore the predictor
-                    for (int i = tid; i < nx; i += NT) y[i] = HB_VEC(c, V_TVL)[i];
-                    lu_valid = false; current_jac = true;
-                }
+                if (tid < 32) tri_factor<NV>(c, cc);
+                c_lu = cc; lu_valid = true;
+                if (tid == 0) cnt[K_NLU]++;
             }
-            if (!converged) {
-                h_loc *= 0.5;
-                change_D<NT>(c, order, 0.5);
-                n_equal = 0; lu_valid = false; cnt.nreject++;
-                continue;
-            }
-            safety = 0.9 * (2 * HB_NEWTON_MAXITER + 1) / (double)(2 * HB_NEWTON_MAXITER + n_iter);
-            double le = 0.0;
-#pragma unroll
-            for (int r = 0; r < CPT; ++r) {
-                const int i = tid + r * NT;
-                if (i < nx) {
-                    scl_[r] = atol + rtol * fabs(y[i]);
-                    const double q = (k_error_const[order] * d_[r]) / scl_[r];
-                    le += q * q;
-                }
-            }
-            error_norm = rms<NT>(c, par_, le);
-            if (error_norm > 1.0) {
-                const double factor = fmax(HB_MIN_FACTOR,
-                                           safety * pow(error_norm, -1.0 / (order + 1)));
-                h_loc *= factor;
-                change_D<NT>(c, order, factor);
-                n_equal = 0; cnt.nreject++;
-            } else accepted = true;
+            k_newton = 0; have_old = false; dy_norm_old = 0.0;
+            state = S_NW;
         }
-        n_equal++;
-        t = t_new;
-        h_abs = h_loc;
-        cnt.nsteps++;
-        double lm = 0.0, lp = 0.0;
-        const bool decide = (n_equal >= order + 1);
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) {
-            const int i = tid + r * NT;
-            if (i < nx) {
-                D[(order + 2) * nxp + i] = d_[r] - D[(order + 1) * nxp + i];
-                D[(order + 1) * nxp + i] = d_[r];
-                for (int k = order; k >= 0; --k) D[k * nxp + i] += D[(k + 1) * nxp + i];
-                if (decide) {
-                    if (order > 1) {
-                        const double q = (k_error_const[order - 1] * D[order * nxp + i]) / scl_[r];
-                        lm += q * q;
-                    }
-                    if (order < HB_MAX_ORDER) {
-                        const double q = (k_error_const[order + 1] * D[(order + 2) * nxp + i]) / scl_[r];
-                        lp += q * q;
-                    }
-                }
-            }
+        if (go == GO_JAC_BEGIN) {
+            // base point is in V_B: copy to V_TVL and V_Y
+            __syncthreads();
+            for (int i = tid; i < nx; i += NT) { const double v = b[i]; ybv[i] = v; y[i] = v; }
+            state = S_JB;
         }
-        if (!decide) continue;
-        double em = INFINITY, ep = INFINITY;
-        if (order > 1) em = rms<NT>(c, par_, lm);
-        if (order < HB_MAX_ORDER) ep = rms<NT>(c, par_, lp);
-        const double fm_ = pow(em, -1.0 / order), fe_ = pow(error_norm, -1.0 / (order + 1)),
-                     fp_ = pow(ep, -1.0 / (order + 2));
-        int delta = -1; double best = fm_;
-        if (fe_ > best) { best = fe_; delta = 0; }
-        if (fp_ > best) { best = fp_; delta = 1; }
-        order += delta;
-        const double factor = fmin(HB_MAX_FACTOR, safety * best);
-        h_abs *= factor;
-        change_D<NT>(c, order, factor);
-        n_equal = 0; lu_valid = false;
     }
-    __syncthreads();
-    return 0;
 }
 
 // RichardsPDE.solve (richards_pde.py:478-537): up to 5 attempts, the noise
 // field damped in place by 0.8 after each failure (quirk Q4); the state of the
 // last attempt is left in V_Y (quirk Q5).  Returns 0 ok / 1 failed.
-template <int NT, int CPT>
+template <int NT, int CPT, bool FULL>
 __device__ inline int solve_window(const DevCtx &c, int col, const Args &a, double t0, double t1,
-                                   const double *y_glob, Counters &cnt, bool &noise_damped)
+                                   const double *y_glob, bool &noise_damped)
 {
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     int trials = HB_N_TRIALS, status = 0;
     while (trials > 0) {
-        status = bdf_attempt<NT, CPT>(c, col, a.precip, a.wtd, a.mode, t0, t1, y_glob, cnt);
+        status = bdf_attempt<NT, CPT, FULL>(c, col, a.precip, a.wtd, a.mode, t0, t1, y_glob);
         if (status == 0) break;
         for (int i = threadIdx.x; i < c.nx; i += NT) HB_VEC(c, V_NR)[i] *= HB_NOISE_DAMP;
         noise_damped = true;
-        trials--; cnt.nfail++;
+        trials--;
+        if (threadIdx.x == 0) reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT))[K_NFAIL]++;
         __syncthreads();
     }
     return status == 0 ? 0 : 1;
 }
 
 // find_wtd(y >= psi_sat) on the nodes (utilities.py:56-99).  One sync inside.
-template <int NT>
+template <int NT, int NV>
 __device__ inline int find_wtd_nodes(const DevCtx &c, int &parity, const double *y)
 {
-    const double psi_sat = HB_X(c, X_PAR)[HB_P_PSI_SAT];
+    const double psi_sat = HB_XA(c, NV, X_PAR)[HB_P_PSI_SAT];
     int deepest = -1;
     for (int i = threadIdx.x; i < c.nx; i += NT)
         if (!(y[i] >= psi_sat)) deepest = i;
-    deepest = block_max_int<NT>(c, parity, deepest);
+    deepest = block_max_int<NT, NV>(c, parity, deepest);
     return (deepest < 0) ? 0 : min(deepest + 1, c.nx - 1);
 }
 
