@@ -47,6 +47,7 @@ EXPORTS = {
     "hb_reset_counters": (ct.c_int, [ct.c_void_p]),
     "hb_wtd_moments_dev": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p]),
     "hb_launch_count": (ct.c_int64, [ct.c_void_p]),
+    "hb_measure_fp64_peak": (ct.c_double, [ct.c_void_p]),
     "hb_rhs": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, ct.c_double, ct.c_int, ct.c_int,
                           ct.c_int, _D, _D]),
     "hb_closure_nodes": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, _D]),
@@ -250,6 +251,13 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.hb_launch_count(self._h))
+
+    def measure_fp64_peak(self):
+        """TFLOP/s of a register-resident DFMA loop (roofline denominator)."""
+        v = float(self.lib.hb_measure_fp64_peak(self._h))
+        if v <= 0:
+            raise HydroB200Error(self.lib.hb_last_error().decode())
+        return v
 
     # -- test hooks ---------------------------------------------------------------
     def rhs(self, col, psi, nrnd, precip, wtd, daylight=0, spinup=0):

@@ -50,6 +50,8 @@ struct DevCtx {
     double *wscal, *fields;
     long long *counters;
     int *queue;
+    int *done;               // [n_cols] finished window-chunks per column (time-slicing)
+    int chunk;               // windows per work item of run_kernel
     unsigned long long seed;
     long long col_offset;
 };
@@ -701,7 +703,8 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
     double dy_norm_old = 0.0, d1_init = 0.0, h0_init = 0.0;
 
     __syncthreads();
-    for (int i = tid; i < nx; i += NT) { const double v = y_glob[i]; y[i] = v; D[i] = v; }
+    // __ldcg: the state may have been written by another SM (time-sliced columns)
+    for (int i = tid; i < nx; i += NT) { const double v = __ldcg(y_glob + i); y[i] = v; D[i] = v; }
 
     for (;;) {
         // ======== the single right-hand-side evaluation ========================

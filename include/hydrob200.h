@@ -108,6 +108,9 @@ int  hb_reset_counters(hb_ctx *ctx);
 int  hb_wtd_moments_dev(hb_ctx *ctx, double *sum_dev, double *sumsq_dev);
 /* Number of this library's kernel launches since hb_create. */
 int64_t hb_launch_count(hb_ctx *ctx);
+/* FP64 roofline denominator: TFLOP/s of a register-resident DFMA loop on this
+ * GPU (burst figure, best of 3). */
+double hb_measure_fp64_peak(hb_ctx *ctx);
 
 /* ---- test hooks: the pieces of the path exposed one by one --------------- */
 /* RichardsPDE.__call__ (richards_pde.py:82-160) for column col at state psi. */
