@@ -334,6 +334,8 @@ struct hb_ctx {
     int64_t launches = 0;
     int sms = 0;
     bool grid_set = false, cols_set = false, forcing_set = false;
+    std::vector<int> h_flags;            // Simulation_Flags bitmask per column (host copy)
+    std::vector<int> h_daylight, h_series;  // forcing daylight flags / series map (host copies)
     int variant = 0;        // 0: <256,2>, 1: <512,2>, 2: <512,3>
     size_t smem_bytes = 0;
     int blocks_per_sm = 1;
@@ -555,6 +557,8 @@ int hb_set_columns(hb_ctx *ctx, int col0, int ncol, const double *par, const dou
     CK(cudaMemcpyAsync((void *)(ctx->d.stat + (size_t)col0 * HB_NSTATIC * nx), stat,
                        (size_t)ncol * HB_NSTATIC * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if ((int)ctx->h_flags.size() != ctx->d.n_cols) ctx->h_flags.assign(ctx->d.n_cols, 0);
+    for (int k = 0; k < ncol; ++k) ctx->h_flags[col0 + k] = (int)par[(size_t)k * HB_NPARAM + HB_P_FLAGS];
     ctx->cols_set = true;
     return 0;
 }
@@ -607,6 +611,8 @@ int hb_set_forcing(hb_ctx *ctx, int n_series, int T, const double *precip, const
     CK(cudaStreamSynchronize(ctx->stream));
     d.precip = p; d.atm = a; d.wtd_idx = w; d.daylight = dl; d.series = s;
     d.n_series = n_series; d.T = T;
+    ctx->h_daylight.assign(daylight, daylight + n);
+    if (series_of_col) ctx->h_series.assign(series_of_col, series_of_col + d.n_cols); else ctx->h_series.clear();
     double *ws;
     if (slot_alloc(ctx, ctx->s_wscal, &ws, (size_t)d.n_cols * T * HB_NWSCAL)) return -1;
     d.wscal = ws; d.fields = nullptr; d.n_out = 0; d.out_stride = 0;
@@ -674,6 +680,30 @@ static int ready(hb_ctx *ctx)
     return 0;
 }
 
+// Sinks that are not implemented on the device must fail loudly, never be
+// skipped: ET acts in daylight rows, HLIFT in night rows (richards_pde.py:
+// 226-302), PREDICT changes the lateral-flow sink (:312-351; it crashes in the
+// reference itself on NumPy 2).  SPINUP disables ET / HLIFT.
+static int sinks_supported(hb_ctx *ctx, int w0, int w1)
+{
+    const DevCtx &d = ctx->d;
+    for (int col = 0; col < d.n_cols; ++col) {
+        const int fl = ctx->h_flags.empty() ? 0 : ctx->h_flags[col];
+        if ((fl & HB_FLAG_PREDICT) && (fl & HB_FLAG_LF))
+            return fail("PREDICT lateral-flow mode is not implemented (the reference itself raises on NumPy 2)");
+        if (!(fl & (HB_FLAG_ET | HB_FLAG_HLIFT))) continue;
+        const int ser = ctx->h_series.empty() ? 0 : ctx->h_series[col];
+        for (int row = (w0 > 1 ? w0 : 1); row < w1; ++row) {
+            const int day = ctx->h_daylight[(size_t)ser * d.T + row];
+            if (day && (fl & HB_FLAG_ET))
+                return fail("ET root-water-uptake sink on daylight rows is not implemented on the device yet");
+            if (!day && (fl & HB_FLAG_HLIFT))
+                return fail("HLIFT hydraulic-redistribution term on night rows is not implemented on the device yet");
+        }
+    }
+    return 0;
+}
+
 static int persistent_grid(hb_ctx *ctx)
 {
     const int cap = ctx->sms * ctx->blocks_per_sm;
@@ -714,6 +744,7 @@ int hb_run(hb_ctx *ctx, int w0, int w1)
     DevCtx &d = ctx->d;
     if (w0 < 0 || w1 > d.T || w0 >= w1) return fail("hb_run: bad window range");
     if (d.noise_mode == HB_NOISE_TAPE && !d.tape) return fail("hb_run: noise not set");
+    if (sinks_supported(ctx, w0, w1)) return -1;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(d.queue, 0, sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(d.done, 0, (size_t)d.n_cols * sizeof(int), ctx->stream));
@@ -837,6 +868,11 @@ int hb_rhs(hb_ctx *ctx, int col, const double *psi, const double *nrnd, double p
     if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
     CK(cudaSetDevice(ctx->device));
     if (hook_in(ctx, 0, psi) || hook_in(ctx, 1, nrnd)) return -1;
+    if (!spinup) {
+        const int fl = ctx->h_flags.empty() ? 0 : ctx->h_flags[col];
+        if (daylight && (fl & HB_FLAG_ET)) return fail("ET sink on daylight rows is not implemented on the device yet");
+        if (!daylight && (fl & HB_FLAG_HLIFT)) return fail("HLIFT term on night rows is not implemented on the device yet");
+    }
     HookArgs h{}; h.mode = HK_RHS; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight; h.spinup = spinup;
     if (run_hook(ctx, h)) return -1;
     if (hook_out(ctx, 2, dydt, ctx->d.nx)) return -1;
@@ -890,6 +926,12 @@ int hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0
     if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
     CK(cudaSetDevice(ctx->device));
     if (hook_in(ctx, 0, y0) || hook_in(ctx, 1, nrnd)) return -1;
+    if (!spinup) {
+        const int fl = ctx->h_flags.empty() ? 0 : ctx->h_flags[col];
+        if ((fl & HB_FLAG_PREDICT) && (fl & HB_FLAG_LF)) return fail("PREDICT lateral-flow mode is not implemented");
+        if (daylight && (fl & HB_FLAG_ET)) return fail("ET sink on daylight rows is not implemented on the device yet");
+        if (!daylight && (fl & HB_FLAG_HLIFT)) return fail("HLIFT term on night rows is not implemented on the device yet");
+    }
     HookArgs h{}; h.mode = HK_WINDOW; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight;
     h.spinup = spinup; h.t0 = t0; h.t1 = t1;
     if (run_hook(ctx, h)) return -1;

@@ -170,6 +170,7 @@ class EnsembleSimulation:
         process group, NCCL) the per-GPU moments are all-reduced over the ranks --
         the only collective of this path; it runs once, after the window loop."""
         import torch
+        from .sharding import reduce_moments
         m = self.mData
         T = m["dim_t"]
         dev = torch.device("cuda", self.device)
@@ -177,13 +178,9 @@ class EnsembleSimulation:
         torch.cuda.synchronize(dev)
         self.ctx.wtd_moments_dev(mom[0].data_ptr(), mom[1].data_ptr())
         self.ctx.sync()
-        count = torch.tensor([float(m["n_cols"])], dtype=torch.float64, device=dev)
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            torch.distributed.all_reduce(mom, group=group)
-            torch.distributed.all_reduce(count, group=group)
-        mean = mom[0] / count
-        var = torch.clamp(mom[1] / count - mean * mean, min=0.0)
-        return mean.cpu().numpy(), var.sqrt().cpu().numpy(), int(count.item())
+        count = torch.full((T,), float(m["n_cols"]), dtype=torch.float64, device=dev)
+        mean, std, count = reduce_moments(count, mom[0], mom[1], group)
+        return mean.cpu().numpy(), std.cpu().numpy(), int(count[0].item())
 
     # ------------------------------------------------------------------ output
     def saveResults(self, path=None):

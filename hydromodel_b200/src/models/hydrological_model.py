@@ -32,12 +32,11 @@ class HydrologicalModel:
         return z, psi, phi
 
     def _retention(self, psi, phi):
-        """theta, effective saturation and the saturated mask."""
+        """theta, effective saturation, the saturated mask and phi - theta_res."""
         delta_s = phi - self.theta_res
         sat = psi >= self.psi_sat
         q = self.theta_res + delta_s * (1.0 + (self.alpha * np.abs(psi)) ** self.n) ** (-self.m)
-        q = np.where(np.broadcast_to(sat, q.shape), np.broadcast_to(phi, q.shape), q) \
-            if q.shape == np.broadcast(sat, phi).shape else q
+        q = np.where(sat, phi, q)
         s_eff = np.clip((q - self.theta_res) / delta_s, 0.0, 1.0)
         return q, s_eff, sat, delta_s
 
@@ -45,7 +44,7 @@ class HydrologicalModel:
         with np.errstate(all="ignore"):
             c = (self.m * self.n) * self.alpha * delta_s * \
                 (s_eff ** (1.0 / self.m + 1.0)) * (self.alpha * np.abs(psi)) ** (self.n - 1.0)
-        c = np.where(np.broadcast_to(sat, c.shape), self.epsilon, c)
+        c = np.where(sat, self.epsilon, c)
         return np.where((c < self.epsilon) | ~np.isfinite(c), self.epsilon, c)
 
     def pressure_head(self, theta, z):

@@ -16,8 +16,7 @@ class vanGenuchten(HydrologicalModel):
         q, s_eff, sat, delta_s = self._retention(psi, phi)
         k_sat = self.k_hc.sat_soil * np.ones(psi.shape)
         K = k_sat * np.sqrt(s_eff) * (1.0 - (1.0 - s_eff ** (1.0 / self.m)) ** self.m) ** self.n
-        K = np.where(np.broadcast_to(sat, K.shape), k_sat, K)
-        K = np.minimum(K, k_sat)
+        K = np.minimum(np.where(sat, k_sat, K), k_sat)
         C = self._capacity(psi, s_eff, sat, delta_s)
         q_inf_max = np.minimum(2.0 * (phi[0] - q[0]) * self.dz, k_sat[0])
         return q, K, C, k_sat, q_inf_max

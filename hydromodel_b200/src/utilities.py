@@ -32,15 +32,21 @@ def find_wtd(y=None):
 
 
 def lerp_table(x_knots, y_knots, x_new):
-    """Piecewise-linear lookup ``slope * (x - x_lo) + y_lo`` on increasing
-    knots.  ``y_knots`` may be 1-D or 2-D ``[n_series, n_knots]``.  Raises
-    ``ValueError`` outside the knot range (as ``interp1d`` does by default)."""
+    """Piecewise-linear lookup on increasing knots with the arithmetic of
+    SciPy's ``interp1d`` (scipy/interpolate/_interpolate.py:487-518): a 1-D table
+    goes through ``slope * (x - x_lo) + y_lo`` (np.interp), a 2-D table
+    ``[n_series, n_knots]`` through the two-weight form
+    ``w * y_hi + (1 - w') * y_lo``.  Raises ``ValueError`` outside the knot range
+    (as ``interp1d`` does by default)."""
     x_knots = np.asarray(x_knots, dtype=float)
     y_knots = np.asarray(y_knots, dtype=float)
     x_new = np.asarray(x_new, dtype=float)
     if np.any(x_new < x_knots[0]) or np.any(x_new > x_knots[-1]):
         raise ValueError("A value in x_new is outside the interpolation range.")
+    if y_knots.ndim == 1:
+        return np.interp(x_new, x_knots, y_knots)
     hi = np.clip(np.searchsorted(x_knots, x_new), 1, x_knots.size - 1)
     lo = hi - 1
-    slope = (y_knots[..., hi] - y_knots[..., lo]) / (x_knots[hi] - x_knots[lo])
-    return slope * (x_new - x_knots[lo]) + y_knots[..., lo]
+    x_lo, x_hi = x_knots[lo], x_knots[hi]
+    return ((x_new - x_lo) / (x_hi - x_lo)) * y_knots[..., hi] + \
+        ((x_hi - x_new) / (x_hi - x_lo)) * y_knots[..., lo]

@@ -1,0 +1,198 @@
+"""
+CPU tests of the host-side mirror of the reference's objects.  The cases follow
+the reference's own unit tests (code/tests/test_*.py: range validation, profile
+bounds, root-pdf normalisation, closure shapes / round trip) and add checks
+against the golden outputs of the reference's closures.
+"""
+import numpy as np
+import pytest
+
+from hydromodel_b200 import pack
+from hydromodel_b200.src.soil_properties import SoilProperties
+from hydromodel_b200.src.water_content import WaterContent
+from hydromodel_b200.src.hydraulic_conductivity import HydraulicConductivity
+from hydromodel_b200.src.porosity import Porosity
+from hydromodel_b200.src.tree_roots import TreeRoots
+from hydromodel_b200.src.utilities import logN_rnd, find_wtd, lerp_table
+from hydromodel_b200.src.models.vrettas_fung import VrettasFung
+from hydromodel_b200.src.models.vanGenuchten import vanGenuchten
+from hydromodel_b200.src.models.hydrological_model import HydrologicalModel
+from helpers import column_from_json, rhs_cases, rhs_configs
+
+
+# ---- value objects (reference tests: test_soil_properties / water_content / hydraulic_conductivity)
+def test_soil_properties_validation():
+    s = SoilProperties()
+    assert s.m == pytest.approx(0.5)
+    for attr, bad in (("n", 0.0), ("alpha", 0.0), ("psi_sat", 1.0), ("epsilon", 0.0)):
+        with pytest.raises(ValueError):
+            setattr(s, attr, bad)
+    with pytest.raises(ValueError):
+        SoilProperties(n=0.0)
+    assert SoilProperties(psi_sat=5.0).psi_sat == 0.0          # constructor clamps
+    assert SoilProperties(epsilon=0.0).epsilon == 1.0e-8
+
+
+def test_water_content_validation():
+    w = WaterContent()
+    with pytest.raises(ValueError):
+        w.max += 1.0
+    with pytest.raises(ValueError):
+        w.min -= 1.0
+    with pytest.raises(ValueError):
+        w.res = w.min
+    assert w._checkValues()
+    assert w.mid == pytest.approx(0.5 * (w.min + w.max))
+    with pytest.raises(ValueError):
+        WaterContent(0.3, 0.1, 0.05)
+    w.wlt, w.flc = -1000.0, 300.0
+    assert (w.wlt, w.flc) == (-1000.0, 300.0)
+
+
+def test_hydraulic_conductivity_validation():
+    k = HydraulicConductivity()
+    for attr in ("sat_soil", "sat_saprolite", "sat_fresh_bedrock"):
+        with pytest.raises(ValueError):
+            setattr(k, attr, 0.0)
+        with pytest.raises(ValueError):
+            HydraulicConductivity(**{attr: -1.0})
+    for attr in ("sigma_noise", "lambda_exponent"):
+        with pytest.raises(ValueError):
+            setattr(k, attr, -0.1)
+    assert HydraulicConductivity(sigma_noise=-3.0).sigma_noise == 0.0
+
+
+# ---- utilities (reference test_utilities.py)
+def test_logn_rnd_mean_and_shapes():
+    rng = np.random.default_rng(0)
+    x = logN_rnd(20.5, 1.0, rng.standard_normal(25000))
+    assert np.mean(x) == pytest.approx(20.5, rel=1e-3)
+    assert logN_rnd(np.ones(7), np.ones(7), np.zeros(7)).shape == (7,)
+    assert logN_rnd(np.ones((5, 3)), np.ones((5, 3)), np.zeros((5, 3))).shape == (5, 3)
+
+
+def test_find_wtd_known_answers():
+    assert find_wtd(np.r_[np.zeros(9, bool), True]) == 9
+    assert find_wtd(np.ones(10, bool)) == 0
+    assert find_wtd(np.array([0, 0, 1, 0, 1, 0, 1, 1, 1, 1], bool)) == 6
+    assert find_wtd(np.array([1, 1, 1, 0, 1, 1, 0, 1, 1, 1], bool)) == 7
+    assert find_wtd(None) is None
+
+
+def test_lerp_table_matches_scipy_interp1d():
+    from scipy.interpolate import interp1d
+    rng = np.random.default_rng(1)
+    xk = np.cumsum(rng.uniform(0.5, 2.0, 40)); yk = rng.standard_normal((3, 40))
+    xq = rng.uniform(xk[0], xk[-1], 200)
+    assert np.array_equal(lerp_table(xk, yk, xq), interp1d(xk, yk)(xq))
+    with pytest.raises(ValueError):
+        lerp_table(xk, yk[0], xk[-1] + 1.0)
+
+
+# ---- porosity / roots (reference test_porosity.py, test_tree_roots.py)
+Z = np.arange(0.0, 2005.0, 5.0)
+LAYERS = (0.0, 50.0, 200.0, 2000.0)
+
+
+@pytest.mark.parametrize("profile", ["Constant", "Linear", "Exponential", "Stratified", "Noisy"])
+def test_porosity_profiles(profile):
+    theta, soil = WaterContent(0.05, 0.30, 0.04, 1500.0, 340.0), SoilProperties()
+    p = Porosity(Z, LAYERS, theta, soil, profile)
+    full = p()
+    assert len(full) == 3 and all(v.shape == Z.shape for v in full)
+    assert np.all(p.profile >= theta.min) and np.all(p.profile <= theta.max)
+    assert np.asarray(p(12.5)).shape == (3,)
+    assert np.asarray(p([12.5, 100.0, 1999.0])).shape == (3, 3)
+    assert np.all(p.wilting_point <= p.field_cap)
+    assert p.layers == LAYERS
+
+
+def test_porosity_errors():
+    theta, soil = WaterContent(), SoilProperties()
+    with pytest.raises(ValueError):
+        Porosity(Z, LAYERS, theta, soil, "Nope")
+    with pytest.raises(ValueError):
+        Porosity(np.array([]), LAYERS, theta, soil, "Constant")
+    with pytest.raises(RuntimeError):
+        Porosity(Z[::-1], LAYERS, theta, soil, "Constant")
+
+
+@pytest.mark.parametrize("model", ["Uniform", "Negative_Exp", "Gamma_pdf", "Mixture"])
+def test_tree_roots_pdf_and_efficiency(model):
+    theta, soil = WaterContent(0.05, 0.30, 0.04, 1500.0, 340.0), SoilProperties()
+    por = Porosity(Z, LAYERS, theta, soil, "Stratified")
+    roots = TreeRoots(200, 5.0, model, por)
+    assert np.sum(roots()) * 5.0 == pytest.approx(1.0, rel=1e-5)
+    zr = np.arange(0.0, 1000.0, 5.0)
+    rho, water = roots.efficiency(np.zeros(zr.size), zr)
+    assert water == 0.0 and np.all(rho == 0.0)
+    rng = np.random.default_rng(2)
+    th = por(zr + 1e-9)[2] + rng.uniform(0.01, 0.2, zr.size)
+    rho, water = roots.efficiency(th, zr + 1e-9)
+    if np.any(rho > 0):
+        assert np.sum(rho) * 5.0 == pytest.approx(1.0, rel=1e-5)
+    with pytest.raises(RuntimeError):
+        roots.efficiency(np.zeros(3), zr)
+    with pytest.raises(ValueError):
+        TreeRoots(200, 5.0, "Nope", por)
+
+
+def test_gamma_pdf_matches_scipy():
+    from scipy.stats import gamma
+    from hydromodel_b200.src.tree_roots import _gamma_pdf
+    x = np.linspace(1, 100, 50)
+    assert np.allclose(_gamma_pdf(x, 2.5, 5.0), gamma.pdf(x, a=2.5, scale=5.0), rtol=1e-13)
+
+
+# ---- closures on the host (reference test_hydrological_models.py + golden outputs)
+def test_host_closures_against_reference(golden):
+    g = golden("rhs_cases.npz")
+    n = 0
+    for cfg in rhs_configs(g):
+        col = column_from_json(g[f"{cfg}/params_json"])
+        o = col["objs"]
+        cls = VrettasFung if o["model_id"] == 0 else vanGenuchten
+        hm = cls(o["soil"], o["porosity"], o["K"], o["theta"].res, o["dz"])
+        for _, psi, nr, precip, wtd, spin, p in list(rhs_cases(g, cfg))[:6]:
+            q, K, C, kb, qinf = hm(psi, col["x"], {"n_rnd": nr})
+            ref = g[p + "nodes"]
+            for mine, r in zip((q, K, C, kb), ref):
+                assert np.allclose(mine, r, rtol=1e-11, atol=0)
+            assert float(qinf) == pytest.approx(float(g[p + "qinf"]), rel=1e-11)
+            n += 1
+    assert n >= 40
+
+
+def test_pressure_head_round_trip_and_shapes():
+    theta, k = WaterContent(0.05, 0.30, 0.04, 1500.0, 340.0), HydraulicConductivity()
+    soil = SoilProperties(psi_sat=-0.0047)
+    por = Porosity(Z, LAYERS, theta, soil, "Stratified")
+    for cls in (VrettasFung, vanGenuchten):
+        hm = cls(soil, por, k, theta.res, 5.0)
+        th0 = 0.8 * por.profile
+        psi, s_eff = hm.pressure_head(th0, Z)
+        assert psi.shape == Z.shape and s_eff.shape == Z.shape
+        q, K, C, kb, qinf = hm(psi, Z, {"n_rnd": np.zeros(Z.size)})
+        assert abs(np.mean(q - th0)) < 0.1                      # the reference's (loose) bar
+        assert np.allclose(q, th0, rtol=1e-9)
+        psi2 = np.repeat(psi[:, None], 4, axis=1)
+        q2, K2, C2, kb2, _ = hm(psi2, Z, {"n_rnd": np.zeros(Z.size)})
+        assert q2.shape == (Z.size, 4)
+        with pytest.raises(ValueError):
+            hm(psi[:-1], Z, {"n_rnd": np.zeros(Z.size)})
+    base = HydrologicalModel(soil, por, k, theta.res, 5.0)
+    sat_psi, _ = base.pressure_head(por.profile, Z)
+    assert np.array_equal(sat_psi, np.arange(Z.size) * 5.0)        # saturated column: spin-up start
+
+
+def test_pack_quirks():
+    """Q1/Q2 bookkeeping of the static pack."""
+    from helpers import default_column
+    col = default_column()
+    par, stat = col["par"], col["stat"]
+    assert par[pack.P_PHI_TOP] == col["objs"]["porosity"].profile[0]
+    assert par[pack.P_DSMIN_ALL] == (col["objs"]["porosity"].profile - col["objs"]["theta"].res).min()
+    assert set(np.unique(stat[pack.S_COEF_MID, :-1])) == {0.05, 0.10, 1.0}
+    assert int(par[pack.P_FLAGS]) == pack.FLAG_LF | pack.FLAG_ET
+    # midpoint 0 (z = 2.5 cm) lies in the soil layer: coefficient 0.05, mean Ksat_soil
+    assert stat[pack.S_COEF_MID, 0] == 0.05 and stat[pack.S_KMEAN_MID, 0] == 8.5
