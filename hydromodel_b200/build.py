@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "lib", "libhydrob200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
               "-std=c++17", "-fmad=false", "-cudart", "static", "-shared",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--split-compile", "0"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def nvcc_path():

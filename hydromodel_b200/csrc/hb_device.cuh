@@ -714,6 +714,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         rhs_eval<NT, CPT, NV>(c, S, precip, wtd, mode, out);
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
         int go = GO_NONE;
+        bool jb_now = false;
 
         if (state == S_NW) {
             // ---- one Newton iteration (solve_bdf_system, bdf.py:41-67) --------
@@ -859,23 +860,14 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             const double h1 = (d1_init <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0_init * 1e-3)
                                                                  : sqrt(0.01 / fmax(d1_init, d2));
             h_abs = fmin(fmin(100.0 * h0_init, h1), fabs(t_bound - t0));
-            for (int i = tid; i < nx; i += NT) b[i] = D[i];          // Jacobian at (t0, y0)
+            // Jacobian at (t0, y0): jac_wrapped's f = fun_single(t0, y0) repeats the
+            // evaluation that produced f0 (same inputs, deterministic), so the base
+            // value is taken from D[1] = f0 instead of a sixth RHS evaluation
+            for (int i = tid; i < nx; i += NT) { const double v = D[i]; ybv[i] = v; fbv[i] = D[nxp + i]; }
             jac_first = (jac_only != 2); jac_init = true;
-            go = GO_JAC_BEGIN;
+            jb_now = true;
         } else if (state == S_JB) {
-            // ---- num_jac: steps from the base value (common.py:320-341) -------
-            for (int i = tid; i < nx; i += NT) {
-                double fc = jac_first ? sqrt(HB_EPS) : fac[i];
-                const double ybi = ybv[i];
-                const double ysc = ((fbv[i] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
-                double h = (ybi + fc * ysc) - ybi;
-                while (h == 0.0) { fc *= 10.0; h = (ybi + fc * ysc) - ybi; }
-                fac[i] = fc; hv[i] = h;
-                vd[i] = 0.0;
-                y[i] = ybi + ((c.grp[i] == 0) ? h : 0.0);
-            }
-            jac_g = 0;
-            state = S_JG;
+            jb_now = true;
         } else {
             // ---- num_jac: differences of group jac_g (common.py:385-443) ------
             const double REJECT = 2.0097183471152322e-14;     // EPS ** 0.875
@@ -930,6 +922,22 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 }
                 jac_g = next_g; state = next_state;
             }
+        }
+
+        if (jb_now) {
+            // ---- num_jac: steps from the base value (common.py:320-341) -------
+            for (int i = tid; i < nx; i += NT) {
+                double fc = jac_first ? sqrt(HB_EPS) : fac[i];
+                const double ybi = ybv[i];
+                const double ysc = ((fbv[i] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
+                double h = (ybi + fc * ysc) - ybi;
+                while (h == 0.0) { fc *= 10.0; h = (ybi + fc * ysc) - ybi; }
+                fac[i] = fc; hv[i] = h;
+                vd[i] = 0.0;
+                y[i] = ybi + ((c.grp[i] == 0) ? h : 0.0);
+            }
+            jac_g = 0;
+            state = S_JG;
         }
 
         if (go == GO_JAC_END) {
