@@ -256,7 +256,10 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
             HB_VEC(c, V_JU)[i] = io[4 * nx + i]; b[i] = io[5 * nx + i];
         }
         __syncthreads();
-        if (tid < 32) { tri_factor<NV>(c, h.c); tri_solve<NV>(c, h.c); }
+        if (tid < 32) {
+            if (c.nxp == 32 * 13) { tri_factor13<NV>(c, h.c); tri_solve13<NV>(c, h.c); }
+            else { tri_factor<NV>(c, h.c); tri_solve<NV>(c, h.c); }
+        }
         __syncthreads();
         for (int i = tid; i < nx; i += NT) io[6 * nx + i] = b[i];
     } else if (h.mode == HK_WINDOW) {
@@ -422,6 +425,9 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     ctx->sms = prop.multiProcessorCount;
     DevCtx &d = ctx->d;
     d.nx = nx; d.nxp = (nx + 1) & ~1; d.n_cols = n_cols;
+    // 385..416 nodes (the reference's 401-node default): pad every vector to
+    // 32 x 13 rows so that the tridiagonal solver runs its unrolled variant
+    if (nx > 32 * 12 && nx <= 32 * 13 && !getenv("HB_NO_TRI13")) d.nxp = 32 * 13;
     d.rtol = 1e-3; d.atol = 1e-3;
     ctx->variant = nx <= 464 ? 0 : (nx <= 512 ? 1 : (nx <= 1024 ? 2 : 3));
     if (const char *v = getenv("HB_VARIANT")) {          // tuning experiments

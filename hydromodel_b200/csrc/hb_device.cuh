@@ -278,6 +278,11 @@ __device__ inline void bind_column(const DevCtx &c, int col)
     for (int i = threadIdx.x; i < HB_NPARAM; i += NT)
         HB_XA(c, NV, X_PAR)[i] = c.par[(size_t)col * HB_NPARAM + i];
     if (threadIdx.x < 8) reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT))[threadIdx.x] = 0;
+    // identity padding rows of the tridiagonal system (see tri_solve_fixed)
+    for (int i = c.nx + threadIdx.x; i < c.nxp; i += NT) {
+        HB_VEC(c, V_JL)[i] = 0.0; HB_VEC(c, V_JD)[i] = 0.0; HB_VEC(c, V_JU)[i] = 0.0;
+        HB_VEC(c, V_B)[i] = 0.0;
+    }
     if (FULL) {
         const int nx = c.nx;
         const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
@@ -527,6 +532,121 @@ __device__ __noinline__ void tri_factor(const DevCtx &c, double cc)
     __syncwarp();
 }
 
+// Fully unrolled variants for a compile-time chunk length M.  The vectors are
+// padded to 32*M rows with identity rows (J = 0, rhs = 0), so every lane owns
+// exactly M rows and the code has no predicates or loops: the serial part of
+// the Newton iteration then is one dependent FMA per row.
+template <int NV, int M>
+__device__ __forceinline__ void tri_factor_fixed(const DevCtx &c, double cc)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = lane * M;
+    const double *jl = HB_VEC(c, V_JL) + s, *jd = HB_VEC(c, V_JD) + s, *ju = HB_VEC(c, V_JU) + s;
+    double *tw = HB_VEC(c, V_TW) + s, *tip = HB_VEC(c, V_TIP) + s, *tvl = HB_VEC(c, V_TVL) + s,
+           *tvr = HB_VEC(c, V_TVR) + s, *pcr = HB_XA(c, NV, X_PCR);
+    double av[M], bv[M], cv[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) { av[r] = -cc * jl[r]; bv[r] = 1.0 - cc * jd[r]; cv[r] = -cc * ju[r]; }
+    double ip = fast_rcp(bv[0]);
+    double g = av[0];
+    bv[0] = ip; tw[0] = 0.0;
+#pragma unroll
+    for (int r = 1; r < M - 1; ++r) {
+        const double w = av[r] * ip;
+        ip = fast_rcp(fma(-w, cv[r - 1], bv[r]));
+        tw[r] = w;
+        g = -w * g;
+        bv[r] = ip; av[r] = g;
+    }
+    double zl = av[M - 2] * bv[M - 2], zr = cv[M - 2] * bv[M - 2];
+    const double vl_last = zl, vr_last = zr;
+    tip[M - 2] = bv[M - 2]; tvl[M - 2] = zl; tvr[M - 2] = zr;
+#pragma unroll
+    for (int r = M - 3; r >= 0; --r) {
+        const double cu = cv[r] * bv[r];
+        zl = fma(-cu, zl, av[r] * bv[r]);
+        zr = -cu * zr;
+        tip[r] = bv[r]; tvl[r] = zl; tvr[r] = zr;
+    }
+    const double ae = av[M - 1], be = bv[M - 1];
+    double ce = cv[M - 1];
+    const double vlf_n = __shfl_down_sync(HB_FULL, zl, 1), vrf_n = __shfl_down_sync(HB_FULL, zr, 1);
+    double A = -ae * vl_last, B = be - ae * vr_last, C;
+    if (lane == 31) { C = 0.0; ce = 0.0; }
+    else { B -= ce * vlf_n; C = -ce * vrf_n; }
+    if (lane == 0) A = 0.0;
+    pcr[11 * 32 + lane] = ae;
+    pcr[12 * 32 + lane] = ce;
+#pragma unroll 1
+    for (int st = 0; st < 5; ++st) {
+        const int d = 1 << st;
+        double Am = __shfl_up_sync(HB_FULL, A, d), Bm = __shfl_up_sync(HB_FULL, B, d),
+               Cm = __shfl_up_sync(HB_FULL, C, d);
+        double Ap = __shfl_down_sync(HB_FULL, A, d), Bp = __shfl_down_sync(HB_FULL, B, d),
+               Cp = __shfl_down_sync(HB_FULL, C, d);
+        if (lane < d) { Am = 0.0; Bm = 1.0; Cm = 0.0; }
+        if (lane + d > 31) { Ap = 0.0; Bp = 1.0; Cp = 0.0; }
+        const double k1 = A * fast_rcp(Bm), k2 = C * fast_rcp(Bp);
+        pcr[(2 * st) * 32 + lane] = k1;
+        pcr[(2 * st + 1) * 32 + lane] = k2;
+        B = B - k1 * Cm - k2 * Ap;
+        A = -k1 * Am;
+        C = -k2 * Cp;
+    }
+    pcr[10 * 32 + lane] = fast_rcp(B);
+    __syncwarp();
+}
+
+template <int NV, int M>
+__device__ __forceinline__ void tri_solve_fixed(const DevCtx &c, double cc)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = lane * M;
+    const double *ju = HB_VEC(c, V_JU) + s, *tw = HB_VEC(c, V_TW) + s, *tip = HB_VEC(c, V_TIP) + s,
+                 *tvl = HB_VEC(c, V_TVL) + s, *tvr = HB_VEC(c, V_TVR) + s, *pcr = HB_XA(c, NV, X_PCR);
+    double *b = HB_VEC(c, V_B) + s;
+    double gv[M], xv[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) gv[r] = b[r];
+#pragma unroll
+    for (int r = 1; r < M - 1; ++r) xv[r] = tw[r];
+#pragma unroll
+    for (int r = 1; r < M - 1; ++r) gv[r] = fma(-xv[r], gv[r - 1], gv[r]);      // forward sweep
+#pragma unroll
+    for (int r = 0; r < M - 1; ++r) {           // off-chain factors of the backward sweep
+        const double ip = tip[r];
+        xv[r] = (-cc * ju[r]) * ip;
+        gv[r] = gv[r] * ip;
+    }
+#pragma unroll
+    for (int r = M - 3; r >= 0; --r) gv[r] = fma(-xv[r], gv[r + 1], gv[r]);     // backward sweep
+    double rho = gv[M - 1];
+    const double zf_n = __shfl_down_sync(HB_FULL, gv[0], 1);
+    rho = fma(-pcr[11 * 32 + lane], gv[M - 2], rho);
+    rho = fma(-pcr[12 * 32 + lane], zf_n, rho);          // pcr[12] is 0 on lane 31
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int d = 1 << st;
+        double rm = __shfl_up_sync(HB_FULL, rho, d);
+        double rp = __shfl_down_sync(HB_FULL, rho, d);
+        if (lane < d) rm = 0.0;
+        if (lane + d > 31) rp = 0.0;
+        rho = fma(-pcr[(2 * st + 1) * 32 + lane], rp, fma(-pcr[(2 * st) * 32 + lane], rm, rho));
+    }
+    const double xi = rho * pcr[10 * 32 + lane];
+    double x_left = __shfl_up_sync(HB_FULL, xi, 1);
+    if (lane == 0) x_left = 0.0;
+    b[M - 1] = xi;
+#pragma unroll
+    for (int r = 0; r < M - 1; ++r) b[r] = fma(-xi, tvr[r], fma(-x_left, tvl[r], gv[r]));
+    __syncwarp();
+}
+
+template <int NV>
+__device__ __noinline__ void tri_factor13(const DevCtx &c, double cc) { tri_factor_fixed<NV, 13>(c, cc); }
+template <int NV>
+__device__ __noinline__ void tri_solve13(const DevCtx &c, double cc) { tri_solve_fixed<NV, 13>(c, cc); }
+
 // Solves in place: V_B holds the rhs on entry, the solution on exit.
 template <int NV>
 __device__ __noinline__ void tri_solve(const DevCtx &c, double cc)
@@ -727,7 +847,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             bool converged = false, stop = false;
             if (!__syncthreads_and(finite)) stop = true;
             else {
-                if (tid < 32) tri_solve<NV>(c, c_lu);
+                if (tid < 32) { if (c.nxp == 32 * 13) tri_solve13<NV>(c, c_lu); else tri_solve<NV>(c, c_lu); }
                 if (tid == 0) cnt[K_NNEWTON]++;
                 __syncthreads();
                 double loc = 0.0;
@@ -1022,7 +1142,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         if (go == GO_NEWTON_BEGIN) {
             if (!lu_valid) {
                 __syncthreads();
-                if (tid < 32) tri_factor<NV>(c, cc);
+                if (tid < 32) { if (c.nxp == 32 * 13) tri_factor13<NV>(c, cc); else tri_factor<NV>(c, cc); }
                 c_lu = cc; lu_valid = true;
                 if (tid == 0) cnt[K_NLU]++;
             }
