@@ -383,11 +383,17 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
 }
 
 // Kernel variants: <threads per column, cells per thread, min CTAs per SM,
-// FULL = static profiles and grid metrics staged in shared memory>.
-//   0: <256,2,2,true>   nx <= 464 (default)
+// FULL = static midpoint profiles staged in shared memory>.  Measured on B200
+// with one binary (1,024 columns x 120 windows, nx = 401), column-windows/s:
+//   <256,2,2,true>  515 K   (default: 19 shared vectors = 66 KB, 128 registers, 2 CTAs/SM)
+//   <256,2,3,true>  441 K   (3 CTAs/SM, 80 registers: spills)
+//   <192,3,3,true>  432 K   (3 CTAs/SM, 96 registers)
+//   <128,4,3,true>  478 K   (3 CTAs/SM, 168 registers)
+// i.e. a third resident column per SM does not pay; only the winner is built.
+//   0: <256,2,2,true>   nx <= 448
 //   1: <256,2,2,false>  nx <= 512
 //   2: <512,2,1,false>  nx <= 1024
-//   3: <512,3,1,false>  nx <= 1152
+//   3: <512,3,1,false>  nx <= 1536
 #define HB_FOR_VARIANT(ctx, STMT)                                   \
     do {                                                            \
         switch ((ctx)->variant) {                                   \
@@ -408,7 +414,7 @@ extern "C" {
 
 const char *hb_last_error(void) { return g_err.c_str(); }
 int hb_version(void) { return 100; }
-int hb_max_nx(void) { return 1152; }
+int hb_max_nx(void) { return 1536; }
 
 hb_ctx *hb_create(int device, int nx, int n_cols)
 {
@@ -429,7 +435,7 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     // 32 x 13 rows so that the tridiagonal solver runs its unrolled variant
     if (nx > 32 * 12 && nx <= 32 * 13 && !getenv("HB_NO_TRI13")) d.nxp = 32 * 13;
     d.rtol = 1e-3; d.atol = 1e-3;
-    ctx->variant = nx <= 464 ? 0 : (nx <= 512 ? 1 : (nx <= 1024 ? 2 : 3));
+    ctx->variant = nx <= 448 ? 0 : (nx <= 512 ? 1 : (nx <= 1024 ? 2 : 3));
     if (const char *v = getenv("HB_VARIANT")) {          // tuning experiments
         const int want = atoi(v);
         if (nx <= 512 && want == 1) ctx->variant = 1;
@@ -475,6 +481,11 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
         if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_, MB_, FL_>, NT_);
     });
     if (rc) { hb_destroy(ctx); return nullptr; }
+    {   // BDF difference tables of the resident CTAs
+        double *db;
+        if (dev_alloc(ctx, &db, (size_t)ctx->sms * ctx->blocks_per_sm * 8 * d.nxp)) { hb_destroy(ctx); return nullptr; }
+        d.dbuf = db;
+    }
     return ctx;
 }
 

@@ -50,6 +50,7 @@ struct DevCtx {
     double *wscal, *fields;
     long long *counters;
     int *queue;
+    double *dbuf;            // [resident CTAs][8][nxp] BDF difference tables
     int *done;               // [n_cols] finished window-chunks per column (time-slicing)
     int chunk;               // windows per work item of run_kernel
     unsigned long long seed;
@@ -62,8 +63,7 @@ extern __shared__ double smem[];
 
 // ---- shared-memory layout: vectors of nxp doubles, then a small area --------
 enum {
-    V_D = 0,                // D[0..7]: BDF difference table
-    V_JL = 8, V_JD, V_JU,   // Jacobian rows: lower, diagonal, upper
+    V_JL = 0, V_JD, V_JU,   // Jacobian rows: lower, diagonal, upper
     V_TW, V_TIP, V_TVL, V_TVR,   // tridiagonal factors (Jacobian scratch as well)
     V_Y,                    // Newton iterate / RHS input
     V_CM, V_FM,             // RHS scratch: C and flux at the midpoints
@@ -71,11 +71,13 @@ enum {
     V_FAC,                  // num_jac step factors
     V_NR,                   // noise field n_rnd of the current window
     V_PSI, V_SCL, V_DD,     // Newton: psi, scale, accumulated correction d
-    NVEC_BASE,              // = 24
+    NVEC_BASE,              // = 16
     V_PHI = NVEC_BASE, V_KM, V_CF,   // static profiles at the midpoints   (FULL only)
-    V_DX, V_ZX, V_XZ,                // grid metrics                       (FULL only)
-    NVEC_FULL               // = 30
+    NVEC_FULL               // = 19
 };
+// The BDF difference table D[0..7] (touched once per step, never inside a
+// Newton iteration) lives in global memory: 8*nxp doubles per resident CTA,
+// L2-resident, each element only ever touched by its owning thread.
 enum {                      // offsets (doubles) inside the small area
     X_RED = 0,              // [2][32] block-reduction slots
     X_RU = 64,              // [36] change_D matrix
@@ -259,13 +261,12 @@ __device__ __forceinline__ Statics statics_of(const DevCtx &c, int col)
     Statics s;
     if (FULL) {
         s.phi = HB_VEC(c, V_PHI); s.km = HB_VEC(c, V_KM); s.cf = HB_VEC(c, V_CF);
-        s.dx = HB_VEC(c, V_DX); s.zx = HB_VEC(c, V_ZX); s.xz = HB_VEC(c, V_XZ);
     } else {
         const double *st = c.stat + (size_t)col * HB_NSTATIC * c.nx;
         s.phi = st + (size_t)HB_S_PHI_MID * c.nx; s.km = st + (size_t)HB_S_KMEAN_MID * c.nx;
         s.cf = st + (size_t)HB_S_COEF_MID * c.nx;
-        s.dx = c.dx; s.zx = c.zx; s.xz = c.xz;
     }
+    s.dx = c.dx; s.zx = c.zx; s.xz = c.xz;        // shared by all columns: L1-resident
     return s;
 }
 
@@ -290,7 +291,6 @@ __device__ inline void bind_column(const DevCtx &c, int col)
             HB_VEC(c, V_PHI)[i] = st[(size_t)HB_S_PHI_MID * nx + i];
             HB_VEC(c, V_KM)[i] = st[(size_t)HB_S_KMEAN_MID * nx + i];
             HB_VEC(c, V_CF)[i] = st[(size_t)HB_S_COEF_MID * nx + i];
-            HB_VEC(c, V_DX)[i] = c.dx[i]; HB_VEC(c, V_ZX)[i] = c.zx[i]; HB_VEC(c, V_XZ)[i] = c.xz[i];
         }
     }
 }
@@ -739,8 +739,8 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
         ru[i * 6 + j] = acc;
     }
     __syncthreads();
-    double *D = HB_VEC(c, V_D);
     const int nxp = c.nxp;
+    double *D = c.dbuf + (size_t)blockIdx.x * 8 * nxp;
     for (int p = tid; p < c.nx; p += NT) {
         double col[6], out[6];
 #pragma unroll
@@ -807,7 +807,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
     const int nx = c.nx, nxp = c.nxp, tid = threadIdx.x;
     const double rtol = c.rtol, atol = c.atol;
     const double newton_tol = fmax(10.0 * HB_EPS / rtol, fmin(0.03, sqrt(rtol)));
-    double *D = HB_VEC(c, V_D), *y = HB_VEC(c, V_Y), *b = HB_VEC(c, V_B);
+    double *D = c.dbuf + (size_t)blockIdx.x * 8 * nxp, *y = HB_VEC(c, V_Y), *b = HB_VEC(c, V_B);
     double *vpsi = HB_VEC(c, V_PSI), *vscl = HB_VEC(c, V_SCL), *vd = HB_VEC(c, V_DD);
     double *fbv = HB_VEC(c, V_TW), *fnv = HB_VEC(c, V_TIP), *ybv = HB_VEC(c, V_TVL),
            *hv = HB_VEC(c, V_TVR), *fac = HB_VEC(c, V_FAC);
@@ -828,8 +828,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
 
     for (;;) {
         // ======== the single right-hand-side evaluation ========================
-        const int out = (state == S_F0) ? V_D + 1 : (state == S_JB) ? V_TW
-                      : (state == S_JG || state == S_JR) ? V_TIP : V_B;
+        const int out = (state == S_JB) ? V_TW : (state == S_JG || state == S_JR) ? V_TIP : V_B;
         __syncthreads();
         rhs_eval<NT, CPT, NV>(c, S, precip, wtd, mode, out);
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
@@ -960,10 +959,11 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             // ---- select_initial_step, first half (common.py:105-115) ----------
             double l0 = 0.0, l1 = 0.0;
             for (int i = tid; i < nx; i += NT) {
-                const double y0 = D[i];
+                const double y0 = D[i], f0 = b[i];
+                D[nxp + i] = f0;                                   // D[1] <- f0 (scaled by h later)
                 const double sc = atol + fabs(y0) * rtol;
                 vscl[i] = sc;
-                const double q0 = y0 / sc, q1 = D[nxp + i] / sc;
+                const double q0 = y0 / sc, q1 = f0 / sc;
                 l0 += q0 * q0; l1 += q1 * q1;
             }
             const double d0 = rms<NT, NV>(c, par_, l0);
