@@ -49,14 +49,14 @@ EXPORTS = {
     "hb_launch_count": (ct.c_int64, [ct.c_void_p]),
     "hb_measure_fp64_peak": (ct.c_double, [ct.c_void_p]),
     "hb_rhs": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, ct.c_double, ct.c_int, ct.c_int,
-                          ct.c_int, _D, _D]),
+                          ct.c_int, ct.c_double, _D, _D, _D]),
     "hb_closure_nodes": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, _D]),
     "hb_num_jac": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, ct.c_double, ct.c_int, ct.c_int,
                               ct.c_int, _D, _D, _D, _D, _D]),
     "hb_tri_solve": (ct.c_int, [ct.c_void_p, _D, _D, _D, ct.c_double, _D, _D]),
     "hb_solve_window": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double, ct.c_double, _D, _D,
-                                   ct.c_double, ct.c_int, ct.c_int, ct.c_int, _D, _L, _D,
-                                   ct.POINTER(ct.c_int)]),
+                                   ct.c_double, ct.c_int, ct.c_int, ct.c_int, ct.c_double, _D, _L,
+                                   _D, _D, ct.POINTER(ct.c_int)]),
 }
 
 COUNTER_NAMES = ("nfev", "njev", "nlu", "nsteps", "nreject", "nfail", "nrhs", "nnewton",
@@ -260,12 +260,15 @@ class Context:
         return v
 
     # -- test hooks ---------------------------------------------------------------
-    def rhs(self, col, psi, nrnd, precip, wtd, daylight=0, spinup=0):
+    def rhs(self, col, psi, nrnd, precip, wtd, daylight=0, spinup=0, atm=0.0, with_transpiration=False):
         psi, nrnd = _f64(psi), _f64(nrnd)
         out = np.empty(self.nx)
-        lat = ct.c_double(0.0)
+        lat, tr = ct.c_double(0.0), ct.c_double(0.0)
         self._ck(self.lib.hb_rhs(self._h, col, _d(psi), _d(nrnd), float(precip), int(wtd),
-                                 int(daylight), int(spinup), _d(out), ct.byref(lat)))
+                                 int(daylight), int(spinup), float(atm), _d(out), ct.byref(lat),
+                                 ct.byref(tr)))
+        if with_transpiration:
+            return out, lat.value, tr.value
         return out, lat.value
 
     def closure_nodes(self, col, psi, nrnd):
@@ -291,17 +294,19 @@ class Context:
         self._ck(self.lib.hb_tri_solve(self._h, _d(dl), _d(d), _d(du), float(c), _d(b), _d(x)))
         return x
 
-    def solve_window(self, col, t0, t1, y0, nrnd, precip, wtd, daylight=0, spinup=0):
+    def solve_window(self, col, t0, t1, y0, nrnd, precip, wtd, daylight=0, spinup=0, atm=0.0):
         """Returns (y_end, stats dict, status, lateral_flow); ``nrnd`` (float64,
-        contiguous) is updated in place when the solver damped it."""
+        contiguous) is updated in place when the solver damped it.  The
+        transpiration of the last RHS evaluation is left in ``self.last_transpiration``."""
         y0 = _f64(y0)
         assert nrnd.dtype == np.float64 and nrnd.flags.c_contiguous
         y_end = np.empty(self.nx)
         stats = np.zeros(NCOUNTER, dtype=np.int64)
-        lat = ct.c_double(0.0)
+        lat, tr = ct.c_double(0.0), ct.c_double(0.0)
         status = ct.c_int(0)
         self._ck(self.lib.hb_solve_window(self._h, col, float(t0), float(t1), _d(y0), _d(nrnd),
                                           float(precip), int(wtd), int(daylight), int(spinup),
-                                          _d(y_end), stats.ctypes.data_as(_L), ct.byref(lat),
-                                          ct.byref(status)))
+                                          float(atm), _d(y_end), stats.ctypes.data_as(_L),
+                                          ct.byref(lat), ct.byref(tr), ct.byref(status)))
+        self.last_transpiration = tr.value
         return y_end, dict(zip(COUNTER_NAMES, stats.tolist())), status.value, lat.value

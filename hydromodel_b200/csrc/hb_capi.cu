@@ -65,7 +65,7 @@ __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row,
     if (tid == 0) {
         ws[HB_W_WTD_EST] = (double)wtd_est;
         ws[HB_W_LATERAL] = solved ? lateral_flow<NT, NV>(c) : 0.0;
-        ws[HB_W_TRANSP] = 0.0;
+        ws[HB_W_TRANSP] = solved ? HB_XA(c, NV, X_MISC)[1] : 0.0;
         ws[HB_W_STATUS] = (double)status;
     }
     if (c.fields && c.out_stride > 0 && (row % c.out_stride == 0 || row == c.T - 1)) {
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
                     Args a;
                     a.precip = p; a.wtd = wtd;
                     a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
+                    a.atm = c.atm ? c.atm[(size_t)ser * c.T + row] : 0.0;
                     bool damped = false;
                     status = solve_window<NT, CPT, FULL>(c, col, a, (double)(row - 1), (double)row, psi_g, damped);
                     if (damped && nr_is_base)
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ 
         __syncthreads();
         Args a;
         a.precip = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T];
-        a.wtd = c.wtd_idx[(size_t)ser * c.T]; a.mode = 2;
+        a.wtd = c.wtd_idx[(size_t)ser * c.T]; a.mode = 2; a.atm = 0.0;
         const double dz = HB_XA(c, NV, X_PAR)[HB_P_DZ];
         int it = 0;
         for (it = 0; it < max_iter; ++it) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ 
 // ---- test hooks ---------------------------------------------------------------
 struct HookArgs {
     int mode, col;
-    double precip, t0, t1, c;
+    double precip, t0, t1, c, atm;
     int wtd, daylight, spinup, first;
     double *io;          // device scratch: [8][nx]
     long long *stats;    // [HB_NCOUNTER + 2]
@@ -231,21 +232,22 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
     double *io = h.io;
     double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR), *b = HB_VEC(c, V_B);
     Args a;
-    a.precip = h.precip; a.wtd = h.wtd; a.mode = h.spinup ? 2 : (h.daylight ? 1 : 0);
+    a.precip = h.precip; a.wtd = h.wtd; a.mode = h.spinup ? 2 : (h.daylight ? 1 : 0); a.atm = h.atm;
+    int parity = 0;
     for (int i = tid; i < nx; i += NT) { y[i] = io[i]; nr[i] = io[nx + i]; }
     __syncthreads();
     if (h.mode == HK_RHS) {
         const Statics S = statics_of<FULL>(c, h.col);
-        rhs_eval<NT, CPT, NV>(c, S, a.precip, a.wtd, a.mode, V_B);
+        rhs_eval<NT, CPT, NV>(c, S, h.col, a.precip, a.wtd, a.mode, a.atm, V_B, parity);
         for (int i = tid; i < nx; i += NT) io[2 * nx + i] = b[i];
         __syncthreads();
-        if (tid == 0) io[3 * nx] = lateral_flow<NT, NV>(c);
+        if (tid == 0) { io[3 * nx] = lateral_flow<NT, NV>(c); io[3 * nx + 1] = HB_XA(c, NV, X_MISC)[1]; }
     } else if (h.mode == HK_NODES) {
         nodes_diag<NT, NV>(c, h.col, io + 2 * nx, io + 3 * nx, io + 4 * nx, io + 5 * nx);
     } else if (h.mode == HK_JAC) {
         // the production state machine, stopped right after the initial Jacobian
         if (!h.first) for (int i = tid; i < nx; i += NT) HB_VEC(c, V_FAC)[i] = io[2 * nx + i];
-        bdf_attempt<NT, CPT, FULL>(c, h.col, a.precip, a.wtd, a.mode, 0.0, 1.0, io, h.first ? 1 : 2);
+        bdf_attempt<NT, CPT, FULL>(c, h.col, a.precip, a.wtd, a.mode, a.atm, 0.0, 1.0, io, h.first ? 1 : 2);
         for (int i = tid; i < nx; i += NT) {
             io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
             io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_VEC(c, V_FAC)[i];
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
         __syncthreads();
         if (tid == 0) {
             io[3 * nx] = lateral_flow<NT, NV>(c);
+            io[3 * nx + 1] = HB_XA(c, NV, X_MISC)[1];
             long long z[HB_NCOUNTER] = {0};
             add_counters(z, reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), 1, false);
             for (int k = 0; k < HB_NCOUNTER; ++k) h.stats[k] = z[k];
@@ -697,26 +700,16 @@ static int ready(hb_ctx *ctx)
     return 0;
 }
 
-// Sinks that are not implemented on the device must fail loudly, never be
-// skipped: ET acts in daylight rows, HLIFT in night rows (richards_pde.py:
-// 226-302), PREDICT changes the lateral-flow sink (:312-351; it crashes in the
-// reference itself on NumPy 2).  SPINUP disables ET / HLIFT.
+// Modes that are not implemented on the device must fail loudly, never be
+// skipped: PREDICT changes the lateral-flow sink (richards_pde.py:312-351; it
+// raises in the reference itself on NumPy 2).
 static int sinks_supported(hb_ctx *ctx, int w0, int w1)
 {
-    const DevCtx &d = ctx->d;
-    for (int col = 0; col < d.n_cols; ++col) {
+    (void)w0; (void)w1;
+    for (int col = 0; col < ctx->d.n_cols; ++col) {
         const int fl = ctx->h_flags.empty() ? 0 : ctx->h_flags[col];
         if ((fl & HB_FLAG_PREDICT) && (fl & HB_FLAG_LF))
             return fail("PREDICT lateral-flow mode is not implemented (the reference itself raises on NumPy 2)");
-        if (!(fl & (HB_FLAG_ET | HB_FLAG_HLIFT))) continue;
-        const int ser = ctx->h_series.empty() ? 0 : ctx->h_series[col];
-        for (int row = (w0 > 1 ? w0 : 1); row < w1; ++row) {
-            const int day = ctx->h_daylight[(size_t)ser * d.T + row];
-            if (day && (fl & HB_FLAG_ET))
-                return fail("ET root-water-uptake sink on daylight rows is not implemented on the device yet");
-            if (!day && (fl & HB_FLAG_HLIFT))
-                return fail("HLIFT hydraulic-redistribution term on night rows is not implemented on the device yet");
-        }
     }
     return 0;
 }
@@ -880,20 +873,19 @@ static int hook_out(hb_ctx *ctx, int slot, double *dst, int n)
 }
 
 int hb_rhs(hb_ctx *ctx, int col, const double *psi, const double *nrnd, double precip, int wtd,
-           int daylight, int spinup, double *dydt, double *lateral_flow)
+           int daylight, int spinup, double atm, double *dydt, double *lateral_flow,
+           double *transpiration)
 {
     if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
     CK(cudaSetDevice(ctx->device));
     if (hook_in(ctx, 0, psi) || hook_in(ctx, 1, nrnd)) return -1;
-    if (!spinup) {
-        const int fl = ctx->h_flags.empty() ? 0 : ctx->h_flags[col];
-        if (daylight && (fl & HB_FLAG_ET)) return fail("ET sink on daylight rows is not implemented on the device yet");
-        if (!daylight && (fl & HB_FLAG_HLIFT)) return fail("HLIFT term on night rows is not implemented on the device yet");
-    }
-    HookArgs h{}; h.mode = HK_RHS; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight; h.spinup = spinup;
+    HookArgs h{}; h.mode = HK_RHS; h.col = col; h.atm = atm; h.precip = precip; h.wtd = wtd; h.daylight = daylight; h.spinup = spinup;
     if (run_hook(ctx, h)) return -1;
     if (hook_out(ctx, 2, dydt, ctx->d.nx)) return -1;
-    if (lateral_flow && hook_out(ctx, 3, lateral_flow, 1)) return -1;
+    double two[2];
+    if (hook_out(ctx, 3, two, 2)) return -1;
+    if (lateral_flow) *lateral_flow = two[0];
+    if (transpiration) *transpiration = two[1];
     return 0;
 }
 
@@ -937,23 +929,24 @@ int hb_tri_solve(hb_ctx *ctx, const double *dl, const double *d, const double *d
 }
 
 int hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0, double *nrnd,
-                    double precip, int wtd, int daylight, int spinup, double *y_end,
-                    int64_t *stats, double *lateral_flow, int *status)
+                    double precip, int wtd, int daylight, int spinup, double atm, double *y_end,
+                    int64_t *stats, double *lateral_flow, double *transpiration, int *status)
 {
     if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
     CK(cudaSetDevice(ctx->device));
     if (hook_in(ctx, 0, y0) || hook_in(ctx, 1, nrnd)) return -1;
-    if (!spinup) {
+    {
         const int fl = ctx->h_flags.empty() ? 0 : ctx->h_flags[col];
         if ((fl & HB_FLAG_PREDICT) && (fl & HB_FLAG_LF)) return fail("PREDICT lateral-flow mode is not implemented");
-        if (daylight && (fl & HB_FLAG_ET)) return fail("ET sink on daylight rows is not implemented on the device yet");
-        if (!daylight && (fl & HB_FLAG_HLIFT)) return fail("HLIFT term on night rows is not implemented on the device yet");
     }
-    HookArgs h{}; h.mode = HK_WINDOW; h.col = col; h.precip = precip; h.wtd = wtd; h.daylight = daylight;
+    HookArgs h{}; h.mode = HK_WINDOW; h.col = col; h.atm = atm; h.precip = precip; h.wtd = wtd; h.daylight = daylight;
     h.spinup = spinup; h.t0 = t0; h.t1 = t1;
     if (run_hook(ctx, h)) return -1;
     if (hook_out(ctx, 2, y_end, ctx->d.nx) || hook_out(ctx, 1, nrnd, ctx->d.nx)) return -1;
-    if (lateral_flow && hook_out(ctx, 3, lateral_flow, 1)) return -1;
+    double two[2];
+    if (hook_out(ctx, 3, two, 2)) return -1;
+    if (lateral_flow) *lateral_flow = two[0];
+    if (transpiration) *transpiration = two[1];
     long long st[HB_NCOUNTER + 2];
     CK(cudaMemcpy(st, ctx->hook_stats, sizeof(st), cudaMemcpyDeviceToHost));
     if (stats) for (int k = 0; k < HB_NCOUNTER; ++k) stats[k] = st[k];

@@ -71,9 +71,10 @@ enum {
     V_FAC,                  // num_jac step factors
     V_NR,                   // noise field n_rnd of the current window
     V_PSI, V_SCL, V_DD,     // Newton: psi, scale, accumulated correction d
-    NVEC_BASE,              // = 16
+    V_TH, V_SK,             // theta and root-uptake sink at the midpoints (ET)
+    NVEC_BASE,              // = 18
     V_PHI = NVEC_BASE, V_KM, V_CF,   // static profiles at the midpoints   (FULL only)
-    NVEC_FULL               // = 19
+    NVEC_FULL               // = 21
 };
 // The BDF difference table D[0..7] (touched once per step, never inside a
 // Newton iteration) lives in global memory: 8*nxp doubles per resident CTA,
@@ -83,11 +84,12 @@ enum {                      // offsets (doubles) inside the small area
     X_RU = 64,              // [36] change_D matrix
     X_PCR = 100,            // [13][32] reduced-system coefficients
     X_PAR = 516,            // [HB_NPARAM] column scalars
-    X_MISC = 516 + HB_NPARAM,    // [8]  0: p_left
+    X_MISC = 516 + HB_NPARAM,    // [8]  0: p_left  1: transpiration of the last RHS  2..: ET scalars
     X_LATW = X_MISC + 8,    // [32] per-warp lateral-flow partial sums
     X_WMAX = X_LATW + 32,   // [32 ints] deepest unsaturated midpoint per warp
     X_CNT = X_WMAX + 16,    // [8 long long] solver counters (thread 0 writes)
-    X_END = X_CNT + 8
+    X_SCAN = X_CNT + 8,     // [32] per-warp totals of the block prefix sum (ET)
+    X_END = X_SCAN + 32
 };
 enum { K_NFEV = 0, K_NJEV, K_NLU, K_NSTEPS, K_NREJECT, K_NFAIL, K_NRHS, K_NNEWTON };
 
@@ -105,6 +107,7 @@ struct Args {
     double precip;          // already scaled by the column's multiplier
     int wtd;                // observed water-table node index
     int mode;
+    double atm;             // atmospheric demand of the row (ET)
 };
 
 // BDF coefficient tables (bdf.py:244-247), filled by the host in double.
@@ -295,6 +298,166 @@ __device__ inline void bind_column(const DevCtx &c, int col)
     }
 }
 
+// Hydraulic redistribution term of the flux, night rows only
+// (richards_pde.py:234-254): f += 0.5 * c_hr * (dpsi/dz * dz) in the root zone.
+__device__ __noinline__ double hydraulic_lift(const DevCtx &c, const double *par, int col, int k,
+                                              double ym, double dy, double flux)
+{
+    const double rootk = c.stat[((size_t)col * HB_NSTATIC + HB_S_ROOT_MID) * c.nx + k];
+    if (!(rootk > 0.0)) return flux;
+    const double one = 1.0 - par[HB_P_IPSI50] * ym;
+    const double c_hr = (1800 * par[HB_P_LAI]) * (one * one) * rootk;
+    return flux + 0.5 * c_hr * (dy * par[HB_P_DZ]);
+}
+
+// alpha_01 * alpha_02 of TreeRoots.efficiency for one cell (tree_roots.py:234-265),
+// before the "all cells flooded" damping; a2 is returned separately.
+__device__ __forceinline__ double root_alphas(double th, double phi, double fcap, double wilt,
+                                              double cum_over_total, double *a2_out)
+{
+    double d01 = phi - wilt;
+    if (d01 == 0.0) d01 = 1.0;
+    const double a1 = fmax(th / d01, cum_over_total);
+    double a2 = 0.0;
+    if (wilt < th && th <= fcap) {
+        double d02 = fcap - wilt;
+        if (d02 == 0.0) d02 = 1.0;
+        a2 = (th - fcap) / d02;
+    }
+    if (th > fcap) a2 = 1.0;
+    *a2_out = fmin(fmax(a2, 0.0), 1.0);
+    return a1;
+}
+
+// Root-water-uptake sink (richards_pde.py:258-302, tree_roots.py:179-292), daylight
+// rows only.  The reference evaluates it once for the top half-cell (one midpoint,
+// its own normalisation) and once for the interior midpoints 1..nx-2; both are
+// reproduced.  theta at the midpoints is in V_TH; the sink goes to V_SK and the
+// integrated transpiration of the interior call to MISC[1].  Block reductions and
+// a block prefix sum inside: all threads must call it.  Cold code, out of line.
+template <int NT, int CPT, int NV>
+__device__ __noinline__ void et_sink(const DevCtx &c, int col, double atm, int &parity)
+{
+    const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *par = HB_XA(c, NV, X_PAR);
+    const double dz = par[HB_P_DZ];
+    const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
+    const double *root = st + (size_t)HB_S_ROOT_MID * nx, *phi = st + (size_t)HB_S_PHI_MID * nx,
+                 *fcap = st + (size_t)HB_S_FCAP_MID * nx, *wilt = st + (size_t)HB_S_WILT_MID * nx;
+    const double *th = HB_VEC(c, V_TH);
+    double *sk = HB_VEC(c, V_SK), *scan = HB_XA(c, NV, X_SCAN), *misc = HB_XA(c, NV, X_MISC);
+
+    // ---- top half-cell call: midpoint 0 alone (thread 0) -----------------------
+    if (tid == 0) {
+        double s0 = 0.0;
+        if (root[0] > 0.0) {
+            double water = (th[0] - wilt[0]) * dz, rho = 0.0;
+            if (water > 0.0) {
+                double a2;
+                // cumsum / total of a single cell: 1, or 0/1 = 0 when theta is zero
+                const double ratio = (th[0] * dz == 0.0) ? 0.0 : 1.0;
+                const double a1s = root_alphas(th[0], phi[0], fcap[0], wilt[0], ratio, &a2);
+                if (a2 == 1.0) a2 *= 0.1;
+                rho = fabs(a1s * a2);
+                double tot = rho * dz;
+                if (tot == 0.0) tot = 1.0;
+                rho /= tot;
+            } else water = 0.0;
+            double x = rho * root[0], totx = x * dz;
+            if (totx > 1.0) { x /= totx; totx = x * dz; }
+            if (totx > 0.0) s0 = -(fmin(atm, water) / totx * x);
+        }
+        sk[0] = s0;
+    }
+
+    // ---- interior call: midpoints 1 .. nx-2 -------------------------------------
+    double thv[CPT], rt[CPT];
+    double lw = 0.0, lt = 0.0;
+#pragma unroll
+    for (int r = 0; r < CPT; ++r) {
+        const int k = tid + r * NT;
+        thv[r] = 0.0; rt[r] = 0.0;
+        if (k >= 1 && k <= nx - 2) {
+            rt[r] = root[k];
+            if (rt[r] > 0.0) { thv[r] = th[k]; lw += thv[r] - wilt[k]; lt += thv[r]; }
+        }
+    }
+    double water = block_sum<NT, NV>(c, parity, lw) * dz;
+    double total = block_sum<NT, NV>(c, parity, lt) * dz;
+    double xv[CPT];
+    if (water > 0.0) {
+        if (total == 0.0) total = 1.0;
+        // inclusive prefix sum of theta over the root cells in depth order
+        double carry = 0.0, a1v[CPT], a2v[CPT], nall = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) {
+            const int k = tid + r * NT;
+            double v = (rt[r] > 0.0) ? thv[r] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(HB_FULL, v, o);
+                if (lane >= o) v += u;
+            }
+            __syncthreads();
+            if (lane == 31) scan[warp] = v;
+            __syncthreads();
+            double before = carry, round_total = 0.0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) {
+                const double t = scan[w];
+                if (w < warp) before += t;
+                round_total += t;
+            }
+            carry += round_total;
+            a1v[r] = 0.0; a2v[r] = 1.0;
+            if (rt[r] > 0.0) {
+                const double cum = (before + v) * dz;
+                a1v[r] = root_alphas(thv[r], phi[k], fcap[k], wilt[k], cum / total, &a2v[r]);
+                if (a2v[r] != 1.0) nall += 1.0;
+            }
+        }
+        const bool all_one = block_sum<NT, NV>(c, parity, nall) == 0.0;
+        double lr = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) {
+            xv[r] = 0.0;
+            if (rt[r] > 0.0) { xv[r] = fabs(a1v[r] * (all_one ? a2v[r] * 0.1 : a2v[r])); lr += xv[r]; }
+        }
+        double tot = block_sum<NT, NV>(c, parity, lr) * dz;
+        if (tot == 0.0) tot = 1.0;
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) xv[r] = (rt[r] > 0.0) ? (xv[r] / tot) * rt[r] : 0.0;
+    } else {
+        water = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) xv[r] = 0.0;
+    }
+    double lx = 0.0;
+#pragma unroll
+    for (int r = 0; r < CPT; ++r) lx += xv[r];
+    double totx = block_sum<NT, NV>(c, parity, lx) * dz;
+    if (totx > 1.0) {
+        lx = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) { xv[r] /= totx; lx += xv[r]; }
+        totx = block_sum<NT, NV>(c, parity, lx) * dz;
+    }
+    double lu = 0.0;
+    const double tr_pot = (totx > 0.0) ? fmin(atm, water) / totx : 0.0;
+#pragma unroll
+    for (int r = 0; r < CPT; ++r) {
+        const int k = tid + r * NT;
+        if (k >= 1 && k < nx) {
+            const double up = (totx > 0.0 && rt[r] > 0.0) ? tr_pot * xv[r] : 0.0;
+            sk[k] = -up;
+            lu += up;
+        }
+    }
+    const double transp = block_sum<NT, NV>(c, parity, lu) * dz;
+    if (tid == 0) misc[1] = transp;
+    __syncthreads();
+}
+
 // Surface evaporation of bc_fun (richards_pde.py:455-468), daylight only: it
 // acts when np.all(theta_left > theta_res) over the profile the porosity call
 // broadcasts to (quirk Q2).  Cold: daily forcing never reaches it.
@@ -315,14 +478,17 @@ __device__ __noinline__ double evaporation(const double *par, double y0)
 // (each thread writes, and may afterwards read, its own cells).  Contains one
 // __syncthreads(); writes V_CM, V_FM and the small slots WMAX, MISC, LATW.
 template <int NT, int CPT, int NV>
-__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, double precip, int wtd,
-                                         int mode, int out)
+__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int col, double precip,
+                                         int wtd, int mode, double atm, int out, int &parity)
 {
     const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *par = HB_XA(c, NV, X_PAR);
     const double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR);
-    double *cm = HB_VEC(c, V_CM), *fm = HB_VEC(c, V_FM);
+    double *cm = HB_VEC(c, V_CM), *fm = HB_VEC(c, V_FM), *thm = HB_VEC(c, V_TH);
     const double psi_sat = par[HB_P_PSI_SAT];
+    const int flags = (int)par[HB_P_FLAGS];
+    const bool et_on = (mode == 1) && (flags & HB_FLAG_ET);        // daylight, not SPINUP
+    const bool hl_on = (mode == 0) && (flags & HB_FLAG_HLIFT);     // night, not SPINUP
     int deepest = -1;                    // deepest unsaturated interior midpoint of this warp
 
     // ---- phase A: closures and fluxes at the midpoints ----------------------
@@ -350,7 +516,10 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, doub
             const Clos cl = closure(par, ym, phi, km, cf, e);
             if (!bnd) {
                 cm[k] = cl.C;
-                fm[k] = cl.K * (dy - 1.0);
+                double fl = cl.K * (dy - 1.0);
+                if (hl_on) fl = hydraulic_lift(c, par, col, k, ym, dy, fl);
+                fm[k] = fl;
+                thm[k] = cl.theta;
                 unsat_interior = (k >= 1) && !(ym >= psi_sat);
             } else {
                 const double q_inf_max = fmin(2.0 * (phi - cl.theta) * par[HB_P_DZ], cl.kb);
@@ -366,10 +535,13 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, doub
     int *wmax = reinterpret_cast<int *>(HB_XA(c, NV, X_WMAX));
     if (lane == 0) wmax[warp] = deepest;
     __syncthreads();
+    if (et_on) et_sink<NT, CPT, NV>(c, col, atm, parity);
+    else if (tid == 0) HB_XA(c, NV, X_MISC)[1] = 0.0;
+    const double *sk = HB_VEC(c, V_SK);
 
     // ---- phase B: lateral-flow sink (monitoring mode) and assembly ----------
     int lo = 1, hi = 0;                  // active sink range in midpoint index: [lo, hi)
-    if (((int)par[HB_P_FLAGS]) & HB_FLAG_LF) {
+    if (flags & HB_FLAG_LF) {
         int kmax = wmax[0];
 #pragma unroll
         for (int w = 1; w < NT / 32; ++w) kmax = max(kmax, wmax[w]);
@@ -385,13 +557,15 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, doub
         const int i = tid + r * NT;
         if (i < nx) {
             const double yi = y[i];
-            double s_i = 0.0, s_m = 0.0;
+            // sink at midpoints i and i-1: root uptake (<= 0, daylight) and, inside
+            // the lateral-flow range, min(alpha_lat * psi_mid, sink)
+            double s_i = (et_on && i < nx - 1) ? sk[i] : 0.0, s_m = (et_on && i >= 1) ? sk[i - 1] : 0.0;
             if (i >= lo && i < hi) {          // own midpoint i
-                s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), 0.0);
+                s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), s_i);
                 lat += fabs(s_i);
             }
             if (i - 1 >= lo && i - 1 < hi)    // midpoint i-1
-                s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), 0.0);
+                s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), s_m);
             // the three node types of richards_pde.py:109-156:
             //   top     (p_left + (f_0 + zx*s_0)) / (zx*C_0)
             //   inner   (f_i - f_{i-1} + (zx*s_i + xz*s_{i-1})) / (zx*C_i + xz*C_{i-1})
@@ -795,8 +969,8 @@ __device__ __noinline__ void column_stats(const double *fb, const double *fn, in
 // ---------------------------------------------------------------------------
 template <int NT, int CPT, bool FULL>
 __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip, int wtd, int mode,
-                                        double t0, double t_bound, const double *y_glob,
-                                        int jac_only = 0)
+                                        double atm, double t0, double t_bound,
+                                        const double *y_glob, int jac_only = 0)
 {
     // jac_only (test hook): 1 = return after the initial Jacobian, 2 = the same
     // but starting from the step factors already in V_FAC.
@@ -830,7 +1004,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         // ======== the single right-hand-side evaluation ========================
         const int out = (state == S_JB) ? V_TW : (state == S_JG || state == S_JR) ? V_TIP : V_B;
         __syncthreads();
-        rhs_eval<NT, CPT, NV>(c, S, precip, wtd, mode, out);
+        rhs_eval<NT, CPT, NV>(c, S, col, precip, wtd, mode, atm, out, par_);
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
         int go = GO_NONE;
         bool jb_now = false;
@@ -1168,7 +1342,7 @@ __device__ inline int solve_window(const DevCtx &c, int col, const Args &a, doub
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     int trials = HB_N_TRIALS, status = 0;
     while (trials > 0) {
-        status = bdf_attempt<NT, CPT, FULL>(c, col, a.precip, a.wtd, a.mode, t0, t1, y_glob);
+        status = bdf_attempt<NT, CPT, FULL>(c, col, a.precip, a.wtd, a.mode, a.atm, t0, t1, y_glob);
         if (status == 0) break;
         for (int i = threadIdx.x; i < c.nx; i += NT) HB_VEC(c, V_NR)[i] *= HB_NOISE_DAMP;
         noise_damped = true;

@@ -73,10 +73,11 @@ class RichardsPDE:
     def __call__(self, t, y, *args):
         a = args[0]
         ctx = self._refresh_scalars()
-        dydt, lat = ctx.rhs(0, np.atleast_1d(y), np.atleast_1d(a["n_rnd"]), a["precipitation"],
-                            a["wtd"], self._daylight(a), int(bool(self.sim_flags["SPINUP"])))
+        dydt, lat, tr = ctx.rhs(0, np.atleast_1d(y), np.atleast_1d(a["n_rnd"]), a["precipitation"],
+                                a["wtd"], self._daylight(a), int(bool(self.sim_flags["SPINUP"])),
+                                atm=float(a.get("atm", 0.0)), with_transpiration=True)
         self.var_arg_out["lateral_flow"] = lat
-        self.var_arg_out["transpiration"] = 0.0
+        self.var_arg_out["transpiration"] = tr
         return dydt
 
     @property
@@ -94,12 +95,12 @@ class RichardsPDE:
             raise ValueError(f" {type(self).__name__}: n_rnd must be a contiguous float64 array.")
         y_end, stats, status, lat = ctx.solve_window(
             0, t_span[0], t_span[1], y0, n_rnd, a["precipitation"], a["wtd"],
-            self._daylight(a), int(bool(self.sim_flags["SPINUP"])))
+            self._daylight(a), int(bool(self.sim_flags["SPINUP"])), atm=float(a.get("atm", 0.0)))
         if status != 0:
             print(f" {type(self).__name__}: The ODE solver failed with message: "
                   f"Required step size is less than spacing between numbers.")
         self.var_arg_out["lateral_flow"] = lat
-        self.var_arg_out["transpiration"] = 0.0
+        self.var_arg_out["transpiration"] = ctx.last_transpiration
         return y_end
 
 

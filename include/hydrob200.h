@@ -115,7 +115,8 @@ double hb_measure_fp64_peak(hb_ctx *ctx);
 /* ---- test hooks: the pieces of the path exposed one by one --------------- */
 /* RichardsPDE.__call__ (richards_pde.py:82-160) for column col at state psi. */
 int  hb_rhs(hb_ctx *ctx, int col, const double *psi, const double *nrnd, double precip,
-            int wtd, int daylight, int spinup, double *dydt, double *lateral_flow);
+            int wtd, int daylight, int spinup, double atm, double *dydt, double *lateral_flow,
+            double *transpiration);
 /* h_model(psi, z, args) on the nodes: out[4][nx] = theta, K, C, K_bkg. */
 int  hb_closure_nodes(hb_ctx *ctx, int col, const double *psi, const double *nrnd,
                       double *out);
@@ -130,8 +131,9 @@ int  hb_tri_solve(hb_ctx *ctx, const double *dl, const double *d, const double *
 /* One RichardsPDE.solve (richards_pde.py:478-537) for column col: y0 -> y_end,
  * nrnd is damped in place on failure; stats[HB_NCOUNTER]. */
 int  hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0,
-                     double *nrnd, double precip, int wtd, int daylight, int spinup,
-                     double *y_end, int64_t *stats, double *lateral_flow, int *status);
+                     double *nrnd, double precip, int wtd, int daylight, int spinup, double atm,
+                     double *y_end, int64_t *stats, double *lateral_flow, double *transpiration,
+                     int *status);
 
 #ifdef __cplusplus
 }

@@ -61,7 +61,8 @@ def find_wtd(sat):
     return int(lib().orc_find_wtd(s.ctypes.data_as(ct.POINTER(ct.c_ubyte)), ct.c_int(s.size)))
 
 
-def rhs(x, par, stat, psi, nrnd, precip, wtd, daylight=0, spinup=0, with_cond=False):
+def rhs(x, par, stat, psi, nrnd, precip, wtd, daylight=0, spinup=0, with_cond=False, atm=0.0,
+        with_transpiration=False):
     """dpsi/dt and the lateral flow.  ``with_cond`` also returns, per node, the
     magnitude sum of the terms whose (cancelling) sum forms dpsi/dt -- the scale
     against which rounding-level differences have to be judged."""
@@ -69,9 +70,13 @@ def rhs(x, par, stat, psi, nrnd, precip, wtd, daylight=0, spinup=0, with_cond=Fa
     out = np.empty_like(psi)
     cond = np.empty_like(psi)
     lat = ct.c_double(0.0)
+    transp = ct.c_double(0.0)
     lib().orc_rhs_c(ct.c_int(x.size), _d(x), _d(par), _d(stat), _d(psi), _d(nrnd),
                     ct.c_double(precip), ct.c_int(int(wtd)), ct.c_int(int(daylight)),
-                    ct.c_int(int(spinup)), _d(out), ct.byref(lat), _d(cond))
+                    ct.c_int(int(spinup)), _d(out), ct.byref(lat), _d(cond), ct.c_double(atm),
+                    ct.byref(transp))
+    if with_transpiration:
+        return out, lat.value, cond, transp.value
     if with_cond:
         return out, lat.value, cond
     return out, lat.value
@@ -100,7 +105,7 @@ def num_jac(x, groups, par, stat, psi, nrnd, precip, wtd, daylight=0, spinup=0, 
 
 
 def solve_window(x, groups, par, stat, t0, t1, y0, nrnd, precip, wtd, daylight=0,
-                 spinup=0, rtol=1e-3, atol=1e-3, max_acc=4096):
+                 spinup=0, rtol=1e-3, atol=1e-3, max_acc=4096, atm=0.0):
     """One RichardsPDE.solve.  ``nrnd`` is damped in place on failure (Q4).
     Returns (y_end, stats dict, status, lateral_flow, accepted times)."""
     x, par, stat, y0 = _c(x), _c(par), _c(stat), _c(y0)
@@ -118,7 +123,7 @@ def solve_window(x, groups, par, stat, t0, t1, y0, nrnd, precip, wtd, daylight=0
         _d(nrnd), ct.c_double(precip), ct.c_int(int(wtd)), ct.c_int(int(daylight)),
         ct.c_int(int(spinup)), _d(y_end),
         stats.ctypes.data_as(ct.POINTER(ct.c_int64)), ct.byref(lat), _d(t_acc),
-        ct.byref(n_acc), ct.c_int(max_acc))
+        ct.byref(n_acc), ct.c_int(max_acc), ct.c_double(atm), None)
     names = ("nfev", "njev", "nlu", "nsteps", "nreject", "nfail", "nrhs", "nnewton", "nwindows")
     return y_end, dict(zip(names, stats.tolist())), st, lat.value, t_acc[:n_acc.value].copy()
 

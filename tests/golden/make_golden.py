@@ -67,7 +67,8 @@ def _taping_solve_ivp(fun, t_span, y0, **kw):
     args = kw["args"][0]
     rec = {"y0": np.array(y0, dtype=float), "n_rnd": np.array(args["n_rnd"]),
            "wtd": int(args["wtd"]), "precip": float(args["precipitation"]),
-           "t0": float(t_span[0])}
+           "t0": float(t_span[0]), "atm": float(args.get("atm", 0.0)),
+           "hour": int(args["time"].hour) if "time" in args else 0}
     sol = _real_solve_ivp(fun, t_span=t_span, y0=y0, **kw)
     rec.update(y_end=sol.y[:, -1].copy(), nfev=sol.nfev, njev=sol.njev,
                nlu=sol.nlu, nsteps=sol.t.size - 1, status=sol.status,
@@ -114,7 +115,7 @@ def tape_to_arrays(tape, prefix=""):
         out[prefix + key] = np.stack([r[key] for r in tape])
     for key in ("wtd", "nfev", "njev", "nlu", "nsteps", "status"):
         out[prefix + key] = np.array([r[key] for r in tape], dtype=np.int64)
-    for key in ("precip", "t0", "lateral_flow", "transpiration"):
+    for key in ("precip", "t0", "lateral_flow", "transpiration", "atm", "hour"):
         out[prefix + key] = np.array([r[key] for r in tape], dtype=float)
     out[prefix + "t_acc"] = np.concatenate([r["t_acc"] for r in tape])
     out[prefix + "t_acc_off"] = np.cumsum([0] + [r["t_acc"].size for r in tape])
@@ -343,3 +344,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+# (tests/golden/make_golden_et.py imports this module for its harness)

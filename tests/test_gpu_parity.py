@@ -45,6 +45,32 @@ def test_rhs_and_closure_against_reference_and_oracle(golden):
     assert n_cases >= 250
 
 
+def test_et_and_hlift_sinks_against_reference_and_oracle(golden):
+    """K7: root-water-uptake sink (daylight rows: block prefix sum + reductions
+    over the root zone) and hydraulic-redistribution flux (night rows)."""
+    g = golden("et_cases.npz")
+    n = n_tr = 0
+    for cfg in sorted({k.split("/")[0] for k in g.files}):
+        col = column_from_json(g[f"{cfg}/params_json"])
+        ctx, _ = make_ctx(col)
+        names = sorted({k.split("/")[1] for k in g.files if k.startswith(cfg + "/case")})
+        for cs in names:
+            p = f"{cfg}/{cs}/"
+            precip, wtd, hour, atm = g[p + "scal"]
+            day = int(6 <= hour < 18)
+            dydt, lat, tr = ctx.rhs(0, g[p + "psi"], g[p + "n_rnd"], float(precip), int(wtd), day, 0,
+                                    atm=float(atm), with_transpiration=True)
+            _, _, cond = oracle.rhs(col["x"], col["par"], col["stat"], g[p + "psi"], g[p + "n_rnd"],
+                                    float(precip), int(wtd), day, 0, with_cond=True, atm=float(atm))
+            assert np.all(np.abs(dydt - g[p + "dydt"]) <= 1e-12 * cond + 1e-300), p
+            ref_tr = float(g[p + "transp"])
+            assert tr == pytest.approx(ref_tr, rel=1e-11, abs=1e-300), p
+            assert lat == pytest.approx(float(g[p + "lat"]), rel=1e-12, abs=1e-300)
+            n += 1; n_tr += ref_tr != 0.0
+        ctx.close()
+    assert n == 200 and n_tr >= 60
+
+
 def test_tridiagonal_partition_solver():
     """K3: (I - cJ) x = b with the warp partition/PCR solver vs a dense solve,
     for several sizes incl. ragged chunking (nx not a multiple of 32)."""

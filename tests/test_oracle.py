@@ -193,3 +193,29 @@ def test_run_driver_matches_window_by_window(golden):
     assert np.array_equal(wscal[:, 0] * 5.0, g["wtd_est_cm"][:T])
     assert fields.shape[0] == 4
     assert np.allclose(fields[1, 1], g["theta_vol"][10], rtol=1e-5)
+
+
+def _et_cases(g, cfg):
+    names = sorted({k.split("/")[1] for k in g.files if k.startswith(cfg + "/case")})
+    for cs in names:
+        p = f"{cfg}/{cs}/"
+        precip, wtd, hour, atm = g[p + "scal"]
+        yield p, g[p + "psi"], g[p + "n_rnd"], float(precip), int(wtd), int(6 <= hour < 18), float(atm)
+
+
+def test_et_and_hlift_sinks_against_reference(golden):
+    """Root-water uptake (daylight) and hydraulic redistribution (night):
+    RichardsPDE.__call__ with the reference's tree-root efficiency
+    (richards_pde.py:225-303, tree_roots.py:179-292), 200 cases over 5 configs."""
+    g = golden("et_cases.npz")
+    n = n_tr = 0
+    for cfg in sorted({k.split("/")[0] for k in g.files}):
+        col = column_from_json(g[f"{cfg}/params_json"])
+        for p, psi, nr, precip, wtd, day, atm in _et_cases(g, cfg):
+            dydt, lat, cond, tr = oracle.rhs(col["x"], col["par"], col["stat"], psi, nr, precip, wtd,
+                                             day, 0, atm=atm, with_transpiration=True)
+            assert np.all(np.abs(dydt - g[p + "dydt"]) <= 1e-12 * cond + 1e-300), p
+            ref_tr = float(g[p + "transp"])
+            assert tr == pytest.approx(ref_tr, rel=1e-12, abs=1e-300)
+            n += 1; n_tr += ref_tr != 0.0
+    assert n == 200 and n_tr >= 60
