@@ -519,7 +519,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
                 double fl = cl.K * (dy - 1.0);
                 if (hl_on) fl = hydraulic_lift(c, par, col, k, ym, dy, fl);
                 fm[k] = fl;
-                thm[k] = cl.theta;
+                if (et_on) thm[k] = cl.theta;
                 unsat_interior = (k >= 1) && !(ym >= psi_sat);
             } else {
                 const double q_inf_max = fmin(2.0 * (phi - cl.theta) * par[HB_P_DZ], cl.kb);
