@@ -33,7 +33,9 @@ def build_library(force=False, verbose=False):
             all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB, SRC]
+    # diagnostic builds (never shipped): phase timers / duplicate-phase probe
+    extra = [f"-D{k}=1" for k in ("HB_PHASE_TIMING", "HB_DUP_PROBE") if os.environ.get(k) == "1"]
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(os.path.dirname(LIB), "build.log"), "w") as fh:

@@ -48,6 +48,7 @@ EXPORTS = {
     "hb_wtd_moments_dev": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p]),
     "hb_launch_count": (ct.c_int64, [ct.c_void_p]),
     "hb_measure_fp64_peak": (ct.c_double, [ct.c_void_p]),
+    "hb_get_phase_cycles": (ct.c_int, [ct.c_void_p, _L]),
     "hb_rhs": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, ct.c_double, ct.c_int, ct.c_int,
                           ct.c_int, ct.c_double, _D, _D, _D]),
     "hb_closure_nodes": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, _D]),
@@ -251,6 +252,11 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.hb_launch_count(self._h))
+
+    def phase_cycles(self):
+        out = np.zeros(16, dtype=np.int64)
+        self._ck(self.lib.hb_get_phase_cycles(self._h, out.ctypes.data_as(_L)))
+        return out
 
     def measure_fp64_peak(self):
         """TFLOP/s of a register-resident DFMA loop (roofline denominator)."""

@@ -159,6 +159,11 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
         if (tid == 0) {
             add_counters(c.counters + (size_t)col * HB_NCOUNTER,
                          reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), windows);
+#if HB_PHASE_TIMING
+            for (int k = 0; k < 15; ++k)
+                atomicAdd(reinterpret_cast<unsigned long long *>(c.phase_cycles) + k,
+                          (unsigned long long)reinterpret_cast<long long *>(HB_XA(c, NV, X_TIME))[k]);
+#endif
             __threadfence();                   // state, noise, counters before the hand-over
             atomicExch(c.done + col, chunk + 1);
         }
@@ -258,12 +263,27 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
             HB_VEC(c, V_JU)[i] = io[4 * nx + i]; b[i] = io[5 * nx + i];
         }
         __syncthreads();
+        // factor once, solve; the solve is repeated (same input) to expose cold-code
+        // effects: cycles of repetition r go to io[7*nx + r] (diagnostic)
+        long long t_f0 = clock64();
         if (tid < 32) {
-            if (c.nxp == 32 * 13) { tri_factor13<NV>(c, h.c); tri_solve13<NV>(c, h.c); }
-            else { tri_factor<NV>(c, h.c); tri_solve<NV>(c, h.c); }
+            tri_factor_warp0<NV, FULL>(c, h.c);
         }
+        long long t_f1 = clock64();
+        for (int rep = 0; rep < 4; ++rep) {
+            __syncthreads();
+            for (int i = tid; i < nx; i += NT) b[i] = io[5 * nx + i];
+            __syncthreads();
+            const long long t0 = clock64();
+            if (tid < 32) {
+                tri_solve_warp0<NV, FULL>(c, h.c);
+            }
+            const long long t1 = clock64();
+            if (tid == 0) io[7 * nx + 1 + rep] = (double)(t1 - t0);
+        }
+        if (tid == 0) io[7 * nx] = (double)(t_f1 - t_f0);
         __syncthreads();
-        for (int i = tid; i < nx; i += NT) io[6 * nx + i] = b[i];
+        for (int i = tid; i < nx; i += NT) io[6 * nx + i] = tri_x<NV, FULL>(c, i);
     } else if (h.mode == HK_WINDOW) {
         bool damped = false;
         const int st = solve_window<NT, CPT, FULL>(c, h.col, a, h.t0, h.t1, io, damped);
@@ -476,7 +496,12 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.x = x; d.dx = dx; d.zx = zx; d.xz = xz; d.grp = grp; d.par = par; d.stat = stat;
     d.psi = psi; d.noise_base = nb; d.queue = queue; d.slot_next = slot; d.counters = cnt;
     d.done = done; d.chunk = 16;
+    { long long *pc; if (dev_alloc(ctx, &pc, 16)) { hb_destroy(ctx); return nullptr; } d.phase_cycles = pc; }
     if (const char *v = getenv("HB_CHUNK")) { const int w = atoi(v); if (w > 0) d.chunk = w; }
+    d.dbg = 0;
+#if HB_DUP_PROBE
+    if (const char *v = getenv("HB_DBG")) d.dbg = atoi(v);
+#endif
     d.noise_mode = HB_NOISE_TAPE; d.n_slots = 0; d.tape = nullptr;
     HB_FOR_VARIANT(ctx, {
         rc = prep_kernel(ctx, hook_kernel<NT_, CPT_, MB_, FL_>, NT_);
@@ -819,6 +844,15 @@ int hb_wtd_moments_dev(hb_ctx *ctx, double *sum_dev, double *sumsq_dev)
 
 int64_t hb_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+int hb_get_phase_cycles(hb_ctx *ctx, int64_t *out16)
+{
+    if (!ctx || !out16) return fail("hb_get_phase_cycles: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out16, ctx->d.phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->d.phase_cycles, 0, 16 * sizeof(long long)));
+    return 0;
+}
+
 double hb_measure_fp64_peak(hb_ctx *ctx)
 {
     if (!ctx) { fail("null ctx"); return -1.0; }
@@ -925,6 +959,11 @@ int hb_tri_solve(hb_ctx *ctx, const double *dl, const double *d, const double *d
         hook_in(ctx, 3, d) || hook_in(ctx, 4, du) || hook_in(ctx, 5, b)) return -1;
     HookArgs h{}; h.mode = HK_TRI; h.col = 0; h.c = c;
     if (run_hook(ctx, h)) return -1;
+    if (getenv("HB_TRI_DEBUG")) {            // cycles: factor, then four repeated solves
+        double t[5];
+        CK(cudaMemcpy(t, ctx->hook_io + (size_t)7 * ctx->d.nx, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[hb_tri_solve] cycles: factor %.0f, solve %.0f %.0f %.0f %.0f\n", t[0], t[1], t[2], t[3], t[4]);
+    }
     return hook_out(ctx, 6, x, ctx->d.nx);
 }
 

@@ -50,12 +50,44 @@ struct DevCtx {
     double *wscal, *fields;
     long long *counters;
     int *queue;
+    long long *phase_cycles; // [16] summed phase timings (HB_PHASE_TIMING builds), else unused
     double *dbuf;            // [resident CTAs][8][nxp] BDF difference tables
     int *done;               // [n_cols] finished window-chunks per column (time-slicing)
     int chunk;               // windows per work item of run_kernel
+    int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice
     unsigned long long seed;
     long long col_offset;
 };
+
+#ifndef HB_PHASE_TIMING
+#define HB_PHASE_TIMING 0
+#endif
+// Phase timing (diagnostic builds only): thread 0 accumulates clock64() deltas
+// between the marks of the integrator loop; the marks include barrier waits.
+#if HB_PHASE_TIMING
+#define HB_TICK(c, NV, id)                                                             \
+    do {                                                                               \
+        if (threadIdx.x == 0) {                                                        \
+            long long *tt_ = reinterpret_cast<long long *>(HB_XA(c, NV, X_TIME));      \
+            const long long now_ = clock64();                                          \
+            tt_[id] += now_ - tt_[15];                                                 \
+            tt_[15] = now_;                                                            \
+        }                                                                              \
+    } while (0)
+#else
+#define HB_TICK(c, NV, id) do { } while (0)
+#endif
+// Diagnostic builds (-DHB_DUP_PROBE=1): phases selected by the bit mask DevCtx.dbg
+// are executed twice (idempotently), so the change in throughput is the in-situ
+// cost of that phase.  Production builds compile none of it.
+#ifndef HB_DUP_PROBE
+#define HB_DUP_PROBE 0
+#endif
+#if HB_DUP_PROBE
+#define HB_DUP(c, bit) (((c).dbg & (bit)) ? 2 : 1)
+#else
+#define HB_DUP(c, bit) 1
+#endif
 
 namespace hb {
 
@@ -74,7 +106,8 @@ enum {
     V_TH, V_SK,             // theta and root-uptake sink at the midpoints (ET)
     NVEC_BASE,              // = 18
     V_PHI = NVEC_BASE, V_KM, V_CF,   // static profiles at the midpoints   (FULL only)
-    NVEC_FULL               // = 21
+    V_TCU,                  // tridiagonal factors: scaled upper entries (FULL only)
+    NVEC_FULL               // = 22
 };
 // The BDF difference table D[0..7] (touched once per step, never inside a
 // Newton iteration) lives in global memory: 8*nxp doubles per resident CTA,
@@ -82,14 +115,15 @@ enum {
 enum {                      // offsets (doubles) inside the small area
     X_RED = 0,              // [2][32] block-reduction slots
     X_RU = 64,              // [36] change_D matrix
-    X_PCR = 100,            // [13][32] reduced-system coefficients
-    X_PAR = 516,            // [HB_NPARAM] column scalars
-    X_MISC = 516 + HB_NPARAM,    // [8]  0: p_left  1: transpiration of the last RHS  2..: ET scalars
+    X_PCR = 100,            // [14][32] reduced-system coefficients + exchange slots
+    X_PAR = 548,            // [HB_NPARAM] column scalars
+    X_MISC = 548 + HB_NPARAM,    // [8]  0: p_left  1: transpiration of the last RHS  2..: ET scalars
     X_LATW = X_MISC + 8,    // [32] per-warp lateral-flow partial sums
     X_WMAX = X_LATW + 32,   // [32 ints] deepest unsaturated midpoint per warp
     X_CNT = X_WMAX + 16,    // [8 long long] solver counters (thread 0 writes)
     X_SCAN = X_CNT + 8,     // [32] per-warp totals of the block prefix sum (ET)
-    X_END = X_SCAN + 32
+    X_TIME = X_SCAN + 32,   // [16 long long] phase cycle counters (HB_PHASE_TIMING builds)
+    X_END = X_TIME + 16
 };
 enum { K_NFEV = 0, K_NJEV, K_NLU, K_NSTEPS, K_NREJECT, K_NFAIL, K_NRHS, K_NNEWTON };
 
@@ -282,6 +316,9 @@ __device__ inline void bind_column(const DevCtx &c, int col)
     for (int i = threadIdx.x; i < HB_NPARAM; i += NT)
         HB_XA(c, NV, X_PAR)[i] = c.par[(size_t)col * HB_NPARAM + i];
     if (threadIdx.x < 8) reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT))[threadIdx.x] = 0;
+#if HB_PHASE_TIMING
+    if (threadIdx.x < 16) reinterpret_cast<long long *>(HB_XA(c, NV, X_TIME))[threadIdx.x] = (threadIdx.x == 15) ? clock64() : 0;
+#endif
     // identity padding rows of the tridiagonal system (see tri_solve_fixed)
     for (int i = c.nx + threadIdx.x; i < c.nxp; i += NT) {
         HB_VEC(c, V_JL)[i] = 0.0; HB_VEC(c, V_JD)[i] = 0.0; HB_VEC(c, V_JU)[i] = 0.0;
@@ -496,9 +533,9 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     // extra cell of the last thread in the last round, where that thread has no
     // midpoint of its own (nx <= NT*CPT), so the closure code exists only once.
 #pragma unroll 1
-    for (int r = 0; r < CPT; ++r) {
-        const int k = tid + r * NT;
-        const bool bnd = (r == CPT - 1) && (tid == NT - 1);
+    for (int r = 0; r < CPT * HB_DUP(c, 4); ++r) {
+        const int k = tid + (r % CPT) * NT;
+        const bool bnd = (r % CPT == CPT - 1) && (tid == NT - 1);
         bool unsat_interior = false;
         if (k < nx - 1 || bnd) {
             double ym, dy = 0.0, e, phi, km, cf;
@@ -530,11 +567,12 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
             }
         }
         const unsigned mask = __ballot_sync(HB_FULL, unsat_interior);
-        if (mask) deepest = max(deepest, (warp << 5) + r * NT + (31 - __clz(mask)));
+        if (mask) deepest = max(deepest, (warp << 5) + (r % CPT) * NT + (31 - __clz(mask)));
     }
     int *wmax = reinterpret_cast<int *>(HB_XA(c, NV, X_WMAX));
     if (lane == 0) wmax[warp] = deepest;
     __syncthreads();
+    HB_TICK(c, NV, 1);                   // closure phase incl. its barrier
     if (et_on) et_sink<NT, CPT, NV>(c, col, atm, parity);
     else if (tid == 0) HB_XA(c, NV, X_MISC)[1] = 0.0;
     const double *sk = HB_VEC(c, V_SK);
@@ -553,8 +591,9 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     double lat = 0.0;
     double *fo = HB_VEC(c, out);
 #pragma unroll 1
-    for (int r = 0; r < CPT; ++r) {
-        const int i = tid + r * NT;
+    for (int r = 0; r < CPT * HB_DUP(c, 8); ++r) {
+        const int i = tid + (r % CPT) * NT;
+        if (HB_DUP_PROBE && r == CPT) lat = 0.0;
         if (i < nx) {
             const double yi = y[i];
             // sink at midpoints i and i-1: root uptake (<= 0, daylight) and, inside
@@ -622,6 +661,17 @@ __device__ __noinline__ double fast_rcp(double x)
     double r = (double)__frcp_rn((float)x);
     double e = fma(-x, r, 1.0); r = fma(r, e, r);
     e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+
+// Inline reciprocal for the unrolled factorisation: hardware seed (about 20
+// bits, exponent range of a double) and two Newton steps.
+__device__ __forceinline__ double rcp_nr(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
     e = fma(-x, r, 1.0); r = fma(r, e, r);
     return r;
 }
@@ -721,26 +771,27 @@ __device__ __forceinline__ void tri_factor_fixed(const DevCtx &c, double cc)
     double av[M], bv[M], cv[M];
 #pragma unroll
     for (int r = 0; r < M; ++r) { av[r] = -cc * jl[r]; bv[r] = 1.0 - cc * jd[r]; cv[r] = -cc * ju[r]; }
-    double ip = fast_rcp(bv[0]);
+    double ip = rcp_nr(bv[0]);
     double g = av[0];
     bv[0] = ip; tw[0] = 0.0;
 #pragma unroll
     for (int r = 1; r < M - 1; ++r) {
         const double w = av[r] * ip;
-        ip = fast_rcp(fma(-w, cv[r - 1], bv[r]));
+        ip = rcp_nr(fma(-w, cv[r - 1], bv[r]));
         tw[r] = w;
         g = -w * g;
         bv[r] = ip; av[r] = g;
     }
+    double *tcu = HB_VEC(c, V_TCU) + s;
     double zl = av[M - 2] * bv[M - 2], zr = cv[M - 2] * bv[M - 2];
     const double vl_last = zl, vr_last = zr;
-    tip[M - 2] = bv[M - 2]; tvl[M - 2] = zl; tvr[M - 2] = zr;
+    tip[M - 2] = bv[M - 2]; tvl[M - 2] = zl; tvr[M - 2] = zr; tcu[M - 2] = zr;
 #pragma unroll
     for (int r = M - 3; r >= 0; --r) {
         const double cu = cv[r] * bv[r];
         zl = fma(-cu, zl, av[r] * bv[r]);
         zr = -cu * zr;
-        tip[r] = bv[r]; tvl[r] = zl; tvr[r] = zr;
+        tip[r] = bv[r]; tvl[r] = zl; tvr[r] = zr; tcu[r] = cu;
     }
     const double ae = av[M - 1], be = bv[M - 1];
     double ce = cv[M - 1];
@@ -760,66 +811,88 @@ __device__ __forceinline__ void tri_factor_fixed(const DevCtx &c, double cc)
                Cp = __shfl_down_sync(HB_FULL, C, d);
         if (lane < d) { Am = 0.0; Bm = 1.0; Cm = 0.0; }
         if (lane + d > 31) { Ap = 0.0; Bp = 1.0; Cp = 0.0; }
-        const double k1 = A * fast_rcp(Bm), k2 = C * fast_rcp(Bp);
+        const double k1 = A * rcp_nr(Bm), k2 = C * rcp_nr(Bp);
         pcr[(2 * st) * 32 + lane] = k1;
         pcr[(2 * st + 1) * 32 + lane] = k2;
         B = B - k1 * Cm - k2 * Ap;
         A = -k1 * Am;
         C = -k2 * Cp;
     }
-    pcr[10 * 32 + lane] = fast_rcp(B);
+    pcr[10 * 32 + lane] = rcp_nr(B);
     __syncwarp();
 }
 
+// Warp 0's part of the solve: local sweeps and the reduced system.  On exit
+// V_B holds the locally eliminated values z of the interior rows and the 32
+// interface unknowns are in the exchange slots; every thread then finishes its
+// own rows with tri_x_fixed (two FMAs per row), so the serial section carries
+// no back-substitution.
 template <int NV, int M>
-__device__ __forceinline__ void tri_solve_fixed(const DevCtx &c, double cc)
+__device__ __forceinline__ void tri_solve_fixed(const DevCtx &c)
 {
     const int lane = threadIdx.x & 31;
     const int s = lane * M;
-    const double *ju = HB_VEC(c, V_JU) + s, *tw = HB_VEC(c, V_TW) + s, *tip = HB_VEC(c, V_TIP) + s,
-                 *tvl = HB_VEC(c, V_TVL) + s, *tvr = HB_VEC(c, V_TVR) + s, *pcr = HB_XA(c, NV, X_PCR);
+    const double *tw = HB_VEC(c, V_TW) + s, *tip = HB_VEC(c, V_TIP) + s, *tcu = HB_VEC(c, V_TCU) + s,
+                 *pcr = HB_XA(c, NV, X_PCR);
     double *b = HB_VEC(c, V_B) + s;
     double gv[M], xv[M];
 #pragma unroll
     for (int r = 0; r < M; ++r) gv[r] = b[r];
 #pragma unroll
     for (int r = 1; r < M - 1; ++r) xv[r] = tw[r];
+    HB_TICK(c, NV, 8);
 #pragma unroll
     for (int r = 1; r < M - 1; ++r) gv[r] = fma(-xv[r], gv[r - 1], gv[r]);      // forward sweep
+    HB_TICK(c, NV, 9);
 #pragma unroll
-    for (int r = 0; r < M - 1; ++r) {           // off-chain factors of the backward sweep
-        const double ip = tip[r];
-        xv[r] = (-cc * ju[r]) * ip;
-        gv[r] = gv[r] * ip;
-    }
+    for (int r = 0; r < M - 1; ++r) { xv[r] = tcu[r]; gv[r] = gv[r] * tip[r]; }
 #pragma unroll
     for (int r = M - 3; r >= 0; --r) gv[r] = fma(-xv[r], gv[r + 1], gv[r]);     // backward sweep
+#pragma unroll
+    for (int r = 0; r < M - 1; ++r) b[r] = gv[r];
+    HB_TICK(c, NV, 10);
     double rho = gv[M - 1];
-    const double zf_n = __shfl_down_sync(HB_FULL, gv[0], 1);
+    // neighbour exchange through shared memory (measured on B200: cheaper than
+    // the shuffle sequence in this single-warp section)
+    double *ex = HB_XA(c, NV, X_PCR) + 13 * 32;
+    ex[lane] = gv[0];
+    __syncwarp();
+    const double zf_n = (lane < 31) ? ex[lane + 1] : 0.0;
+    __syncwarp();
     rho = fma(-pcr[11 * 32 + lane], gv[M - 2], rho);
     rho = fma(-pcr[12 * 32 + lane], zf_n, rho);          // pcr[12] is 0 on lane 31
 #pragma unroll
     for (int st = 0; st < 5; ++st) {
         const int d = 1 << st;
-        double rm = __shfl_up_sync(HB_FULL, rho, d);
-        double rp = __shfl_down_sync(HB_FULL, rho, d);
-        if (lane < d) rm = 0.0;
-        if (lane + d > 31) rp = 0.0;
+        ex[lane] = rho;
+        __syncwarp();
+        const double rm = (lane >= d) ? ex[lane - d] : 0.0;
+        const double rp = (lane + d <= 31) ? ex[lane + d] : 0.0;
+        __syncwarp();
         rho = fma(-pcr[(2 * st + 1) * 32 + lane], rp, fma(-pcr[(2 * st) * 32 + lane], rm, rho));
     }
-    const double xi = rho * pcr[10 * 32 + lane];
-    double x_left = __shfl_up_sync(HB_FULL, xi, 1);
-    if (lane == 0) x_left = 0.0;
-    b[M - 1] = xi;
-#pragma unroll
-    for (int r = 0; r < M - 1; ++r) b[r] = fma(-xi, tvr[r], fma(-x_left, tvl[r], gv[r]));
+    HB_TICK(c, NV, 11);
+    ex[lane] = rho * pcr[10 * 32 + lane];
     __syncwarp();
+    HB_TICK(c, NV, 12);
+}
+
+// Row i of the solution after tri_solve_fixed (any thread, after a barrier).
+template <int NV, int M>
+__device__ __forceinline__ double tri_x_fixed(const DevCtx &c, int i)
+{
+    const int l = i / M, r = i - l * M;
+    const double *xs = HB_XA(c, NV, X_PCR) + 13 * 32;
+    const double xi = xs[l];
+    if (r == M - 1) return xi;
+    const double x_left = (l == 0) ? 0.0 : xs[l - 1];
+    return fma(-xi, HB_VEC(c, V_TVR)[i], fma(-x_left, HB_VEC(c, V_TVL)[i], HB_VEC(c, V_B)[i]));
 }
 
 template <int NV>
 __device__ __noinline__ void tri_factor13(const DevCtx &c, double cc) { tri_factor_fixed<NV, 13>(c, cc); }
 template <int NV>
-__device__ __noinline__ void tri_solve13(const DevCtx &c, double cc) { tri_solve_fixed<NV, 13>(c, cc); }
+__device__ __noinline__ void tri_solve13(const DevCtx &c) { tri_solve_fixed<NV, 13>(c); }
 
 // Solves in place: V_B holds the rhs on entry, the solution on exit.
 template <int NV>
@@ -886,6 +959,28 @@ __device__ __noinline__ void tri_solve(const DevCtx &c, double cc)
     for (int r = s; r < e; ++r)
         b[r] = fma(-xi, tvr[r], fma(-x_left, tvl[r], b[r]));
     __syncwarp();
+}
+
+// Dispatch: the unrolled 13-row variant needs the padded 416-row layout and the
+// extra factor vector of the FULL layout; everything else takes the generic
+// solver (which also does its own back-substitution).
+template <int NV, bool FULL>
+__device__ __forceinline__ bool tri_is13(const DevCtx &c) { return FULL && c.nxp == 32 * 13; }
+template <int NV, bool FULL>
+__device__ __forceinline__ void tri_factor_warp0(const DevCtx &c, double cc)
+{
+    if (FULL && c.nxp == 32 * 13) tri_factor13<NV>(c, cc); else tri_factor<NV>(c, cc);
+}
+template <int NV, bool FULL>
+__device__ __forceinline__ void tri_solve_warp0(const DevCtx &c, double cc)
+{
+    if (FULL && c.nxp == 32 * 13) tri_solve13<NV>(c); else tri_solve<NV>(c, cc);
+}
+template <int NV, bool FULL>
+__device__ __forceinline__ double tri_x(const DevCtx &c, int i)
+{
+    if (FULL && c.nxp == 32 * 13) return tri_x_fixed<NV, 13>(c, i);
+    return HB_VEC(c, V_B)[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -1004,7 +1099,12 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         // ======== the single right-hand-side evaluation ========================
         const int out = (state == S_JB) ? V_TW : (state == S_JG || state == S_JR) ? V_TIP : V_B;
         __syncthreads();
+#if HB_DUP_PROBE
+        if (c.dbg & 8192) { __syncthreads(); __syncthreads(); }
+#endif
+        HB_TICK(c, NV, 0);                   // controller glue since the last mark + loop-top barrier
         rhs_eval<NT, CPT, NV>(c, S, col, precip, wtd, mode, atm, out, par_);
+        HB_TICK(c, NV, 2);                   // assembly phase
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
         int go = GO_NONE;
         bool jb_now = false;
@@ -1017,21 +1117,46 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 finite &= isfinite(f);
                 b[i] = cc * f - vpsi[i] - vd[i];
             }
+#if HB_DUP_PROBE
+            if (c.dbg & 128) { double *s2 = HB_VEC(c, V_SK); for (int i = tid; i < nx; i += NT) s2[i] = cc * b[i] - vpsi[i] - vd[i]; }
+#endif
             bool converged = false, stop = false;
             if (!__syncthreads_and(finite)) stop = true;
             else {
-                if (tid < 32) { if (c.nxp == 32 * 13) tri_solve13<NV>(c, c_lu); else tri_solve<NV>(c, c_lu); }
+                HB_TICK(c, NV, 3);           // residual + barrier
+#if HB_DUP_PROBE
+                if (c.dbg & 3) {             // bit 0: a second solve; bit 1: only its copies and barriers
+                    double *s1 = HB_VEC(c, V_TH), *s2 = HB_VEC(c, V_SK);
+                    for (int i = tid; i < nx; i += NT) s1[i] = b[i];
+                    __syncthreads();
+                    if ((c.dbg & 1) && tid < 32) tri_solve_warp0<NV, FULL>(c, c_lu);
+                    __syncthreads();
+                    for (int i = tid; i < nx; i += NT) { s2[i] = b[i]; b[i] = s1[i]; }
+                    __syncthreads();
+                }
+#endif
+                if (tid < 32) tri_solve_warp0<NV, FULL>(c, c_lu);
                 if (tid == 0) cnt[K_NNEWTON]++;
                 __syncthreads();
+                HB_TICK(c, NV, 4);           // tridiagonal solve + barrier
                 double loc = 0.0;
+#if HB_DUP_PROBE
+                if (c.dbg & 256) { double *s1 = HB_VEC(c, V_TH), *s2 = HB_VEC(c, V_SK);
+                    for (int i = tid; i < nx; i += NT) { const double dy = b[i]; const double q = hb_div(dy, vscl[i]); loc += q * q; s1[i] = y[i] + dy; s2[i] = vd[i] + dy; }
+                    loc = 0.0; }
+#endif
                 for (int i = tid; i < nx; i += NT) {
-                    const double dy = b[i];
+                    const double dy = tri_x<NV, FULL>(c, i);
                     const double q = hb_div(dy, vscl[i]);
                     loc += q * q;
                     y[i] += dy;                    // tentative: discarded if we stop
                     vd[i] += dy;
                 }
+#if HB_DUP_PROBE
+                if (c.dbg & 16) (void)rms<NT, NV>(c, par_, loc);
+#endif
                 const double dy_norm = rms<NT, NV>(c, par_, loc);
+                HB_TICK(c, NV, 5);           // update + norm
                 double rate = 0.0;
                 if (have_old) {
                     rate = hb_div(dy_norm, dy_norm_old);
@@ -1071,12 +1196,16 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 const double safety = 0.9 * (2 * HB_NEWTON_MAXITER + 1) /
                                       (double)(2 * HB_NEWTON_MAXITER + n_iter);
                 double le = 0.0;
+                for (int rp_ = 0; rp_ < HB_DUP(c, 512); ++rp_) { le = 0.0;
                 for (int i = tid; i < nx; i += NT) {
                     const double sc = atol + rtol * fabs(y[i]);
                     vscl[i] = sc;
                     const double q = hb_div(k_error_const[order] * vd[i], sc);
                     le += q * q;
-                }
+                } }
+#if HB_DUP_PROBE
+                if (c.dbg & 512) (void)rms<NT, NV>(c, par_, le);
+#endif
                 const double error_norm = rms<NT, NV>(c, par_, le);
                 if (error_norm > 1.0) {
                     const double factor = fmax(HB_MIN_FACTOR, safety * inv_root(error_norm, order + 1));
@@ -1092,6 +1221,13 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                     h_abs = h_loc;
                     if (tid == 0) cnt[K_NSTEPS]++;
                     const bool decide = (n_equal >= order + 1);
+#if HB_DUP_PROBE
+                    if (c.dbg & 1024) { double *s2 = HB_VEC(c, V_SK);
+                        for (int i = tid; i < nx; i += NT) { double a = vd[i] - D[(order + 1) * nxp + i];
+                            for (int kk = order; kk >= 0; --kk) a += D[kk * nxp + i] + D[(kk + 1) * nxp + i];
+                            s2[i] = a; D[7 * nxp + i] = a; } }
+                    if (c.dbg & 2048) change_D<NT, NV>(c, order, 1.0);
+#endif
                     double lm = 0.0, lp = 0.0;
                     for (int i = tid; i < nx; i += NT) {
                         const double di = vd[i];
@@ -1166,6 +1302,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             // ---- num_jac: differences of group jac_g (common.py:385-443) ------
             const double REJECT = 2.0097183471152322e-14;     // EPS ** 0.875
             __syncthreads();
+            for (int rp_ = 0; rp_ < ((state == S_JG) ? HB_DUP(c, 4096) : 1); ++rp_)
             for (int j = tid; j < nx; j += NT) {
                 if (c.grp[j] != jac_g) continue;
                 if (state == S_JG) {
@@ -1300,6 +1437,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             // ---- predictor, scale, psi (bdf.py:360-366) ----------------------
             cc = hb_div(t_new - t, k_alpha[order]);
             __syncthreads();
+            for (int rp_ = 0; rp_ < HB_DUP(c, 32); ++rp_)
             for (int i = tid; i < nx; i += NT) {
                 double acc = D[i], ps = 0.0;
                 for (int kk = 1; kk <= order; ++kk) {
@@ -1316,9 +1454,12 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         if (go == GO_NEWTON_BEGIN) {
             if (!lu_valid) {
                 __syncthreads();
-                if (tid < 32) { if (c.nxp == 32 * 13) tri_factor13<NV>(c, cc); else tri_factor<NV>(c, cc); }
+                HB_TICK(c, NV, 6);           // step control + predictor
+                for (int rp_ = 0; rp_ < HB_DUP(c, 64); ++rp_)
+                if (tid < 32) tri_factor_warp0<NV, FULL>(c, cc);
                 c_lu = cc; lu_valid = true;
                 if (tid == 0) cnt[K_NLU]++;
+                HB_TICK(c, NV, 7);           // tridiagonal factorisation (warp 0)
             }
             k_newton = 0; have_old = false; dy_norm_old = 0.0;
             state = S_NW;

@@ -108,6 +108,10 @@ int  hb_reset_counters(hb_ctx *ctx);
 int  hb_wtd_moments_dev(hb_ctx *ctx, double *sum_dev, double *sumsq_dev);
 /* Number of this library's kernel launches since hb_create. */
 int64_t hb_launch_count(hb_ctx *ctx);
+/* Diagnostic builds (-DHB_PHASE_TIMING=1) only: cycles thread 0 spent in each
+ * phase of the integrator loop, summed over the columns since the last call;
+ * all zero in production builds. */
+int  hb_get_phase_cycles(hb_ctx *ctx, int64_t *out16);
 /* FP64 roofline denominator: TFLOP/s of a register-resident DFMA loop on this
  * GPU (burst figure, best of 3). */
 double hb_measure_fp64_peak(hb_ctx *ctx);

@@ -40,6 +40,15 @@ for rep in range(3):
     cn = ctx.get_counters().sum(axis=0)
     print("rep %d: %.3f s  -> %.1f column-windows/s  %.2f column-years/s ; per window nfev %.1f njev %.2f nlu %.1f steps %.1f rhs %.1f fails %d" % (
         rep, dt, C * (T - 1) / dt, C * (T - 1) / dt / 365.0, cn[0] / cn[8], cn[1] / cn[8], cn[2] / cn[8], cn[3] / cn[8], cn[6] / cn[8], cn[5]))
+pc = ctx.phase_cycles()
+if pc[:8].sum() > 0:
+    names = ["glue+top barrier", "closure phase", "assembly", "residual", "tri solve", "update+norm", "step ctl+predictor", "tri factor"]
+    tot = pc[:8].sum()
+    print("phase cycles of thread 0 (all columns, last rep): " + ", ".join(f"{n} {100*v/tot:.1f}%" for n, v in zip(names, pc[:8])))
+    print("cycles per column-window: %.0f" % (tot / (C * (T - 1))))
+    cn2 = ctx.get_counters().sum(axis=0)
+    sub = ["loads", "fwd sweep", "scale+bwd", "PCR", "backsub"]
+    print("tri_solve per call (cycles): " + ", ".join(f"{n} {pc[8+k]/max(cn2[7],1):.0f}" for k, n in enumerate(sub)), " | whole phase 4 per call: %.0f" % (pc[4] / max(cn2[7], 1)))
 w = ctx.get_wscal()
 print("wtd_est spread at end:", np.unique(w[:, -1, 0])[:10])
 ctx.close()
