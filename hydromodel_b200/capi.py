@@ -79,7 +79,8 @@ def load():
         return _lib
     path = _build.LIB
     try:
-        path = _build.build_library()
+        # HB_LIB_PATH: an alternative build of the same library (A/B experiments)
+        path = os.environ.get("HB_LIB_PATH") or _build.build_library()
     except RuntimeError:
         if not os.path.exists(path):
             raise HydroB200Error(
