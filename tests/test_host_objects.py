@@ -196,3 +196,75 @@ def test_pack_quirks():
     assert int(par[pack.P_FLAGS]) == pack.FLAG_LF | pack.FLAG_ET
     # midpoint 0 (z = 2.5 cm) lies in the soil layer: coefficient 0.05, mean Ksat_soil
     assert stat[pack.S_COEF_MID, 0] == 0.05 and stat[pack.S_KMEAN_MID, 0] == 8.5
+
+
+# ----------------------------------------------------------------------------- HDF5 files
+def _h5_sample():
+    rng = np.random.default_rng(5)
+    return {"psi_press": rng.standard_normal((14, 401)), "status": rng.integers(0, 3, 365).astype(np.int8),
+            "counters": rng.integers(0, 1 << 40, (4, 9)), "empty": np.zeros((0, 5)),
+            "scalar": np.float64(3.5), "f32": rng.standard_normal((3, 4, 5)).astype(np.float32),
+            "u16": (np.arange(70000) % 65536).astype(np.uint16), "flag": np.array([True, False, True]),
+            "wtd_est_cm": np.round(rng.uniform(500, 1100, (6, 41)))}
+
+
+def test_hdf5_writer_reader_round_trip(tmp_path):
+    """Result files without h5py: every dataset comes back with its
+    shape, dtype and bits; gzip level 4 like h5py's compression='gzip'."""
+    import struct
+    import zlib
+    from hydromodel_b200.src import hdf5_min
+    data = _h5_sample()
+    for kwargs in ({}, {"compression_level": None}, {"chunk_rows": 3}):
+        path = str(tmp_path / "out.h5")
+        hdf5_min.write_file(path, data, **kwargs)
+        back = hdf5_min.read_file(path)
+        assert sorted(back) == sorted(data)
+        for k, v in data.items():
+            v = np.asarray(v)
+            want = v.astype(np.uint8) if v.dtype == np.bool_ else v
+            assert back[k].shape == want.shape and back[k].dtype == want.dtype, (k, kwargs)
+            assert np.array_equal(back[k], want), (k, kwargs)
+        buf = open(path, "rb").read()
+        # superblock version 0: signature, 8-byte offsets and lengths, end-of-file address
+        assert buf[:8] == b"\x89HDF\r\n\x1a\n" and buf[8] == 0 and buf[13] == 8 and buf[14] == 8
+        assert struct.unpack_from("<Q", buf, 40)[0] == len(buf) and len(buf) % 8 == 0
+        root_oh, = struct.unpack_from("<Q", buf, 64)
+        assert buf[root_oh] == 1 and struct.unpack_from("<H", buf, root_oh + 16)[0] == 0x0011
+    # the chunk of a compressed dataset is a plain zlib stream of the C-ordered array
+    path = str(tmp_path / "one.h5")
+    arr = np.arange(12.0).reshape(3, 4)
+    hdf5_min.write_file(path, {"a": arr})
+    buf = open(path, "rb").read()
+    comp = zlib.compress(arr.tobytes(), 4)
+    assert buf.count(comp) == 1 and buf.find(comp) % 8 == 0
+
+
+def test_hdf5_reader_rejects_what_it_does_not_understand(tmp_path):
+    from hydromodel_b200.src import hdf5_min
+    p = tmp_path / "bad.h5"
+    p.write_bytes(b"not an hdf5 file at all")
+    with pytest.raises(hdf5_min.HDF5FormatError):
+        hdf5_min.read_file(str(p))
+    good = str(tmp_path / "good.h5")
+    hdf5_min.write_file(good, {"a": np.arange(100.0)})
+    buf = bytearray(open(good, "rb").read())
+    (tmp_path / "trunc.h5").write_bytes(bytes(buf[:len(buf) - 64]))
+    with pytest.raises(hdf5_min.HDF5FormatError):
+        hdf5_min.read_file(str(tmp_path / "trunc.h5"))
+    buf[8] = 3                                             # superblock version 3
+    (tmp_path / "v3.h5").write_bytes(bytes(buf))
+    with pytest.raises(hdf5_min.HDF5FormatError):
+        hdf5_min.read_file(str(tmp_path / "v3.h5"))
+    with pytest.raises(hdf5_min.HDF5FormatError):
+        hdf5_min.write_file(str(tmp_path / "x.h5"), {"s": np.array(["text"])})
+
+
+def test_save_and_load_results_like_the_reference(tmp_path):
+    """Simulation.saveResults / loadResults (simulation.py:674-746) on top of it."""
+    from hydromodel_b200.src.hdf5_io import load_datasets, save_datasets
+    data = {k: v for k, v in _h5_sample().items() if k != "flag"}
+    path = save_datasets(str(tmp_path / "Sim_00.h5"), data)
+    assert path.endswith("Sim_00.h5")
+    back = load_datasets(path)
+    assert all(np.array_equal(back[k], np.asarray(v)) for k, v in data.items())
