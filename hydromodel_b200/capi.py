@@ -168,9 +168,18 @@ class Context:
         psi = _f64(psi).reshape(-1, self.nx)
         self._ck(self.lib.hb_set_state(self._h, col0, psi.shape[0], _d(psi)))
 
-    def get_state(self, col0=0, ncol=None):
+    @staticmethod
+    def _out(out, shape):
+        """Caller-provided result buffer (e.g. pinned host memory) or a fresh array."""
+        if out is None:
+            return np.empty(shape)
+        if out.shape != tuple(shape) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float64 array of shape {tuple(shape)}")
+        return out
+
+    def get_state(self, col0=0, ncol=None, out=None):
         ncol = self.n_cols - col0 if ncol is None else ncol
-        out = np.empty((ncol, self.nx))
+        out = self._out(out, (ncol, self.nx))
         self._ck(self.lib.hb_get_state(self._h, col0, ncol, _d(out)))
         return out
 
@@ -226,15 +235,15 @@ class Context:
     def run(self, w0=0, w1=None):
         self._ck(self.lib.hb_run(self._h, int(w0), int(self.T if w1 is None else w1)))
 
-    def get_wscal(self, col0=0, ncol=None):
+    def get_wscal(self, col0=0, ncol=None, out=None):
         ncol = self.n_cols - col0 if ncol is None else ncol
-        out = np.empty((ncol, self.T, NWSCAL))
+        out = self._out(out, (ncol, self.T, NWSCAL))
         self._ck(self.lib.hb_get_wscal(self._h, col0, ncol, _d(out)))
         return out
 
-    def get_fields(self, col0=0, ncol=None):
+    def get_fields(self, col0=0, ncol=None, out=None):
         ncol = self.n_cols - col0 if ncol is None else ncol
-        out = np.empty((ncol, self.n_output_rows, NFIELD, self.nx))
+        out = self._out(out, (ncol, self.n_output_rows, NFIELD, self.nx))
         self._ck(self.lib.hb_get_fields(self._h, col0, ncol, _d(out)))
         return out
 

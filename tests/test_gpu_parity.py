@@ -276,4 +276,11 @@ def test_error_paths():
         ctx.set_grid(col["x"][::-1].copy(), grp)     # decreasing grid
     with pytest.raises(capi.HydroB200Error):
         capi.Context(5000, 1)                # nx beyond the shared-memory design
+    # results can be read into caller-owned (e.g. pinned) buffers of the right shape only
+    psi = np.full((1, col["x"].size), -100.0)
+    ctx.set_state(psi)
+    buf = np.empty_like(psi)
+    assert ctx.get_state(out=buf) is buf and np.array_equal(buf, psi)
+    with pytest.raises(ValueError):
+        ctx.get_state(out=np.empty((2, 3)))
     ctx.close()
