@@ -40,6 +40,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# dram__bytes_read.sum (365.1 MB) + dram__bytes_write.sum (686.1 MB) of run_kernel<256,2,2,true> for
+# (columns, rows, out_stride, nx) below: 2.5x the 413 MB of algorithmic bytes -- the time-sliced
+# scheduler hands state and noise field of a column over through HBM every 16 rows (+150 MB each
+# way) and the L2 writes back difference-table / stack lines; 1.3 GB/s in total, 2e-4 of the HBM peak
+NCU_TRAFFIC = {"workload": (1024, 365, 30, 401), "bytes": 365125888 + 686119424,
+               "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"}
+
+
 # ----------------------------------------------------------------------------- workload
 def build_workload(n_cols, first_col, n_rows, total_cols):
     """Pack `n_cols` ensemble members (global ids first_col..) and the shared forcing."""
@@ -370,6 +378,11 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     ach_tf = flops / (step_ms * 1e-3) / 1e12
+    # DRAM bytes of one run_kernel launch from the committed `ncu --set full` capture of this
+    # very workload (dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
+    traffic, traffic_src = None, None
+    if (a.columns, a.rows, a.out_stride, nx) == NCU_TRAFFIC["workload"]:
+        traffic, traffic_src = NCU_TRAFFIC["bytes"], NCU_TRAFFIC["source"]
     ach_gbs = abytes / (step_ms * 1e-3) / 1e9
     csum = counters.sum(axis=0).astype(float)
     result = {
@@ -390,7 +403,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_fp64, "unit": "TFLOP/s",
-                     "frac": ach_tf / peak_fp64, "traffic": None,
+                     "frac": ach_tf / peak_fp64, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (read + write)", "traffic_source": traffic_src,
                      "peak_source": "hb_measure_fp64_peak: register-resident DFMA loop measured in "
                                     "this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "flops_per_launch": flops,
