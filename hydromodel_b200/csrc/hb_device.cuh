@@ -89,6 +89,12 @@ struct DevCtx {
 #define HB_DUP(c, bit) 1
 #endif
 
+// The cells of this thread (i = tid, tid + NT, ...) with a compile-time trip count, used in
+// the per-step and per-Newton-iteration loops: the iterations are unrolled so that the loads of
+// all cells are issued before the first dependent arithmetic (+3 % measured; converting the
+// remaining, colder loops as well made the kernel smaller but 2.5 % slower -- left alone).
+#define HB_FOR_CELLS(i) _Pragma("unroll") for (int r_ = 0; r_ < CPT; ++r_) if (const int i = tid + r_ * NT; i < nx)
+
 namespace hb {
 
 extern __shared__ double smem[];
@@ -590,7 +596,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     }
     double lat = 0.0;
     double *fo = HB_VEC(c, out);
-#pragma unroll 1
+#pragma unroll
     for (int r = 0; r < CPT * HB_DUP(c, 8); ++r) {
         const int i = tid + (r % CPT) * NT;
         if (HB_DUP_PROBE && r == CPT) lat = 0.0;
@@ -986,7 +992,7 @@ __device__ __forceinline__ double tri_x(const DevCtx &c, int i)
 // ---------------------------------------------------------------------------
 // change_D (SCIPY bdf.py:18-33): D[0..order] <- (R U)^T D[0..order].
 // ---------------------------------------------------------------------------
-template <int NT, int NV>
+template <int NT, int CPT, int NV>
 __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
 {
     const int tid = threadIdx.x;
@@ -1010,7 +1016,8 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
     __syncthreads();
     const int nxp = c.nxp;
     double *D = c.dbuf + (size_t)blockIdx.x * 8 * nxp;
-    for (int p = tid; p < c.nx; p += NT) {
+    const int nx = c.nx;
+    HB_FOR_CELLS(p) {
         double col[6], out[6];
 #pragma unroll
         for (int j = 0; j < 6; ++j) col[j] = (j < q) ? D[j * nxp + p] : 0.0;
@@ -1112,7 +1119,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         if (state == S_NW) {
             // ---- one Newton iteration (solve_bdf_system, bdf.py:41-67) --------
             bool finite = true;
-            for (int i = tid; i < nx; i += NT) {
+            HB_FOR_CELLS(i) {
                 const double f = b[i];
                 finite &= isfinite(f);
                 b[i] = cc * f - vpsi[i] - vd[i];
@@ -1145,7 +1152,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                     for (int i = tid; i < nx; i += NT) { const double dy = b[i]; const double q = hb_div(dy, vscl[i]); loc += q * q; s1[i] = y[i] + dy; s2[i] = vd[i] + dy; }
                     loc = 0.0; }
 #endif
-                for (int i = tid; i < nx; i += NT) {
+                HB_FOR_CELLS(i) {
                     const double dy = tri_x<NV, FULL>(c, i);
                     const double q = hb_div(dy, vscl[i]);
                     loc += q * q;
@@ -1186,7 +1193,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                     go = GO_JAC_BEGIN;
                 } else {
                     h_loc *= 0.5;
-                    change_D<NT, NV>(c, order, 0.5);
+                    change_D<NT, CPT, NV>(c, order, 0.5);
                     n_equal = 0; lu_valid = false;
                     if (tid == 0) cnt[K_NREJECT]++;
                     go = GO_STEP_RETRY;
@@ -1197,7 +1204,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                                       (double)(2 * HB_NEWTON_MAXITER + n_iter);
                 double le = 0.0;
                 for (int rp_ = 0; rp_ < HB_DUP(c, 512); ++rp_) { le = 0.0;
-                for (int i = tid; i < nx; i += NT) {
+                HB_FOR_CELLS(i) {
                     const double sc = atol + rtol * fabs(y[i]);
                     vscl[i] = sc;
                     const double q = hb_div(k_error_const[order] * vd[i], sc);
@@ -1210,7 +1217,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 if (error_norm > 1.0) {
                     const double factor = fmax(HB_MIN_FACTOR, safety * inv_root(error_norm, order + 1));
                     h_loc *= factor;
-                    change_D<NT, NV>(c, order, factor);
+                    change_D<NT, CPT, NV>(c, order, factor);
                     n_equal = 0;
                     if (tid == 0) cnt[K_NREJECT]++;
                     go = GO_STEP_RETRY;
@@ -1226,10 +1233,10 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                         for (int i = tid; i < nx; i += NT) { double a = vd[i] - D[(order + 1) * nxp + i];
                             for (int kk = order; kk >= 0; --kk) a += D[kk * nxp + i] + D[(kk + 1) * nxp + i];
                             s2[i] = a; D[7 * nxp + i] = a; } }
-                    if (c.dbg & 2048) change_D<NT, NV>(c, order, 1.0);
+                    if (c.dbg & 2048) change_D<NT, CPT, NV>(c, order, 1.0);
 #endif
                     double lm = 0.0, lp = 0.0;
-                    for (int i = tid; i < nx; i += NT) {
+                    HB_FOR_CELLS(i) {
                         const double di = vd[i];
                         D[(order + 2) * nxp + i] = di - D[(order + 1) * nxp + i];
                         D[(order + 1) * nxp + i] = di;
@@ -1259,7 +1266,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                         order += delta;
                         const double factor = fmin(HB_MAX_FACTOR, safety * best);
                         h_abs *= factor;
-                        change_D<NT, NV>(c, order, factor);
+                        change_D<NT, CPT, NV>(c, order, factor);
                         n_equal = 0; lu_valid = false;
                     }
                     go = GO_STEP_BEGIN;
@@ -1409,7 +1416,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
             if (h_abs < min_step) {
                 h_loc = min_step;
-                change_D<NT, NV>(c, order, min_step / h_abs);
+                change_D<NT, CPT, NV>(c, order, min_step / h_abs);
                 n_equal = 0;
             } else h_loc = h_abs;
             current_jac = false;
@@ -1427,7 +1434,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             t_new = t + h_loc;
             if (t_new - t_bound > 0.0) {
                 t_new = t_bound;
-                change_D<NT, NV>(c, order, fabs(t_new - t) / h_loc);
+                change_D<NT, CPT, NV>(c, order, fabs(t_new - t) / h_loc);
                 n_equal = 0; lu_valid = false;
             }
             h_loc = fabs(t_new - t);
@@ -1438,7 +1445,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             cc = hb_div(t_new - t, k_alpha[order]);
             __syncthreads();
             for (int rp_ = 0; rp_ < HB_DUP(c, 32); ++rp_)
-            for (int i = tid; i < nx; i += NT) {
+            HB_FOR_CELLS(i) {
                 double acc = D[i], ps = 0.0;
                 for (int kk = 1; kk <= order; ++kk) {
                     const double dk = D[kk * nxp + i];
