@@ -1346,7 +1346,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             }
             if (done) go = GO_JAC_END;
             else {
-                for (int i = tid; i < nx; i += NT) {
+                HB_FOR_CELLS(i) {
                     double step = 0.0;
                     if (c.grp[i] == next_g) {
                         if (next_state == S_JG) step = hv[i];
@@ -1364,7 +1364,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
 
         if (jb_now) {
             // ---- num_jac: steps from the base value (common.py:320-341) -------
-            for (int i = tid; i < nx; i += NT) {
+            HB_FOR_CELLS(i) {
                 double fc = jac_first ? sqrt(HB_EPS) : fac[i];
                 const double ybi = ybv[i];
                 const double ysc = ((fbv[i] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
@@ -1394,7 +1394,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 fac[j] = fmax(fc, 1e3 * HB_EPS);
             }
             __syncthreads();
-            for (int i = tid; i < nx; i += NT) {
+            HB_FOR_CELLS(i) {
                 jl[i] = (i > 0) ? fnv[i - 1] : 0.0;
                 ju[i] = (i < nx - 1) ? fbv[i + 1] : 0.0;
             }
