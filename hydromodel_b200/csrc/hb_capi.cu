@@ -251,11 +251,11 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
         nodes_diag<NT, NV>(c, h.col, io + 2 * nx, io + 3 * nx, io + 4 * nx, io + 5 * nx);
     } else if (h.mode == HK_JAC) {
         // the production state machine, stopped right after the initial Jacobian
-        if (!h.first) for (int i = tid; i < nx; i += NT) HB_VEC(c, V_FAC)[i] = io[2 * nx + i];
+        if (!h.first) for (int i = tid; i < nx; i += NT) HB_GROW(c, G_FAC)[i] = io[2 * nx + i];
         bdf_attempt<NT, CPT, FULL>(c, h.col, a.precip, a.wtd, a.mode, a.atm, 0.0, 1.0, io, h.first ? 1 : 2);
         for (int i = tid; i < nx; i += NT) {
             io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
-            io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_VEC(c, V_FAC)[i];
+            io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_GROW(c, G_FAC)[i];
         }
     } else if (h.mode == HK_TRI) {
         for (int i = tid; i < nx; i += NT) {
@@ -398,6 +398,8 @@ template <typename K>
 static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
 {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    if (const char *v = getenv("HB_CARVEOUT"))            // tuning experiments: shared-memory carve-out in percent
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nt, ctx->smem_bytes));
     if (nb < 1) return fail("kernel does not fit on an SM");
@@ -509,9 +511,9 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
         if (!rc) rc = prep_kernel(ctx, run_kernel<NT_, CPT_, MB_, FL_>, NT_);
     });
     if (rc) { hb_destroy(ctx); return nullptr; }
-    {   // BDF difference tables of the resident CTAs
+    {   // per-CTA global scratch of the resident CTAs (difference table, step factors, ET vectors)
         double *db;
-        if (dev_alloc(ctx, &db, (size_t)ctx->sms * ctx->blocks_per_sm * 8 * d.nxp)) { hb_destroy(ctx); return nullptr; }
+        if (dev_alloc(ctx, &db, (size_t)ctx->sms * ctx->blocks_per_sm * hb::G_ROWS * d.nxp)) { hb_destroy(ctx); return nullptr; }
         d.dbuf = db;
     }
     return ctx;

@@ -51,7 +51,7 @@ struct DevCtx {
     long long *counters;
     int *queue;
     long long *phase_cycles; // [16] summed phase timings (HB_PHASE_TIMING builds), else unused
-    double *dbuf;            // [resident CTAs][8][nxp] BDF difference tables
+    double *dbuf;            // [resident CTAs][G_ROWS][nxp] per-CTA global scratch (difference table, ...)
     int *done;               // [n_cols] finished window-chunks per column (time-slicing)
     int chunk;               // windows per work item of run_kernel
     int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice
@@ -106,15 +106,25 @@ enum {
     V_Y,                    // Newton iterate / RHS input
     V_CM, V_FM,             // RHS scratch: C and flux at the midpoints
     V_B,                    // linear-system rhs / solution, RHS output
-    V_FAC,                  // num_jac step factors
     V_NR,                   // noise field n_rnd of the current window
     V_PSI, V_SCL, V_DD,     // Newton: psi, scale, accumulated correction d
-    V_TH, V_SK,             // theta and root-uptake sink at the midpoints (ET)
-    NVEC_BASE,              // = 18
+    NVEC_BASE,              // = 15
     V_PHI = NVEC_BASE, V_KM, V_CF,   // static profiles at the midpoints   (FULL only)
-    V_TCU,                  // tridiagonal factors: scaled upper entries (FULL only)
-    NVEC_FULL               // = 22
+    NVEC_FULL               // = 18
 };
+// Shared memory is kept to 18 vectors (64 KiB at nx = 401) on purpose: two resident
+// CTAs then fit the 132 KiB carve-out and leave 124 KiB of L1 for the difference
+// tables and the register-spill stack -- the kernel is measurably sensitive to L1
+// capacity (28 / 60 / 92 KiB of L1: 424 K / 463 K / 511 K column-windows/s).
+// Vectors that are touched rarely or only by their owning thread live in a
+// per-CTA global scratch instead (rows of DevCtx.dbuf):
+enum {
+    G_D = 0,                // rows 0..7: BDF difference table D[0..7]
+    G_FAC = 8,              // num_jac step factors (Jacobian build only)
+    G_TH = 9, G_SK = 10,    // theta and root-uptake sink at the midpoints (ET rows only)
+    G_ROWS = 11
+};
+#define HB_GROW(c, k) ((c).dbuf + ((size_t)blockIdx.x * hb::G_ROWS + (k)) * (c).nxp)
 // The BDF difference table D[0..7] (touched once per step, never inside a
 // Newton iteration) lives in global memory: 8*nxp doubles per resident CTA,
 // L2-resident, each element only ever touched by its owning thread.
@@ -387,8 +397,8 @@ __device__ __noinline__ void et_sink(const DevCtx &c, int col, double atm, int &
     const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
     const double *root = st + (size_t)HB_S_ROOT_MID * nx, *phi = st + (size_t)HB_S_PHI_MID * nx,
                  *fcap = st + (size_t)HB_S_FCAP_MID * nx, *wilt = st + (size_t)HB_S_WILT_MID * nx;
-    const double *th = HB_VEC(c, V_TH);
-    double *sk = HB_VEC(c, V_SK), *scan = HB_XA(c, NV, X_SCAN), *misc = HB_XA(c, NV, X_MISC);
+    const double *th = HB_GROW(c, G_TH);
+    double *sk = HB_GROW(c, G_SK), *scan = HB_XA(c, NV, X_SCAN), *misc = HB_XA(c, NV, X_MISC);
 
     // ---- top half-cell call: midpoint 0 alone (thread 0) -----------------------
     if (tid == 0) {
@@ -527,7 +537,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *par = HB_XA(c, NV, X_PAR);
     const double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR);
-    double *cm = HB_VEC(c, V_CM), *fm = HB_VEC(c, V_FM), *thm = HB_VEC(c, V_TH);
+    double *cm = HB_VEC(c, V_CM), *fm = HB_VEC(c, V_FM), *thm = HB_GROW(c, G_TH);
     const double psi_sat = par[HB_P_PSI_SAT];
     const int flags = (int)par[HB_P_FLAGS];
     const bool et_on = (mode == 1) && (flags & HB_FLAG_ET);        // daylight, not SPINUP
@@ -581,7 +591,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     HB_TICK(c, NV, 1);                   // closure phase incl. its barrier
     if (et_on) et_sink<NT, CPT, NV>(c, col, atm, parity);
     else if (tid == 0) HB_XA(c, NV, X_MISC)[1] = 0.0;
-    const double *sk = HB_VEC(c, V_SK);
+    const double *sk = HB_GROW(c, G_SK);
 
     // ---- phase B: lateral-flow sink (monitoring mode) and assembly ----------
     int lo = 1, hi = 0;                  // active sink range in midpoint index: [lo, hi)
@@ -788,16 +798,15 @@ __device__ __forceinline__ void tri_factor_fixed(const DevCtx &c, double cc)
         g = -w * g;
         bv[r] = ip; av[r] = g;
     }
-    double *tcu = HB_VEC(c, V_TCU) + s;
     double zl = av[M - 2] * bv[M - 2], zr = cv[M - 2] * bv[M - 2];
     const double vl_last = zl, vr_last = zr;
-    tip[M - 2] = bv[M - 2]; tvl[M - 2] = zl; tvr[M - 2] = zr; tcu[M - 2] = zr;
+    tip[M - 2] = bv[M - 2]; tvl[M - 2] = zl; tvr[M - 2] = zr;
 #pragma unroll
     for (int r = M - 3; r >= 0; --r) {
         const double cu = cv[r] * bv[r];
         zl = fma(-cu, zl, av[r] * bv[r]);
         zr = -cu * zr;
-        tip[r] = bv[r]; tvl[r] = zl; tvr[r] = zr; tcu[r] = cu;
+        tip[r] = bv[r]; tvl[r] = zl; tvr[r] = zr;
     }
     const double ae = av[M - 1], be = bv[M - 1];
     double ce = cv[M - 1];
@@ -834,11 +843,11 @@ __device__ __forceinline__ void tri_factor_fixed(const DevCtx &c, double cc)
 // own rows with tri_x_fixed (two FMAs per row), so the serial section carries
 // no back-substitution.
 template <int NV, int M>
-__device__ __forceinline__ void tri_solve_fixed(const DevCtx &c)
+__device__ __forceinline__ void tri_solve_fixed(const DevCtx &c, double cc)
 {
     const int lane = threadIdx.x & 31;
     const int s = lane * M;
-    const double *tw = HB_VEC(c, V_TW) + s, *tip = HB_VEC(c, V_TIP) + s, *tcu = HB_VEC(c, V_TCU) + s,
+    const double *tw = HB_VEC(c, V_TW) + s, *tip = HB_VEC(c, V_TIP) + s, *ju = HB_VEC(c, V_JU) + s,
                  *pcr = HB_XA(c, NV, X_PCR);
     double *b = HB_VEC(c, V_B) + s;
     double gv[M], xv[M];
@@ -851,7 +860,7 @@ __device__ __forceinline__ void tri_solve_fixed(const DevCtx &c)
     for (int r = 1; r < M - 1; ++r) gv[r] = fma(-xv[r], gv[r - 1], gv[r]);      // forward sweep
     HB_TICK(c, NV, 9);
 #pragma unroll
-    for (int r = 0; r < M - 1; ++r) { xv[r] = tcu[r]; gv[r] = gv[r] * tip[r]; }
+    for (int r = 0; r < M - 1; ++r) { const double ip = tip[r]; xv[r] = (-cc * ju[r]) * ip; gv[r] = gv[r] * ip; }
 #pragma unroll
     for (int r = M - 3; r >= 0; --r) gv[r] = fma(-xv[r], gv[r + 1], gv[r]);     // backward sweep
 #pragma unroll
@@ -898,7 +907,7 @@ __device__ __forceinline__ double tri_x_fixed(const DevCtx &c, int i)
 template <int NV>
 __device__ __noinline__ void tri_factor13(const DevCtx &c, double cc) { tri_factor_fixed<NV, 13>(c, cc); }
 template <int NV>
-__device__ __noinline__ void tri_solve13(const DevCtx &c) { tri_solve_fixed<NV, 13>(c); }
+__device__ __noinline__ void tri_solve13(const DevCtx &c, double cc) { tri_solve_fixed<NV, 13>(c, cc); }
 
 // Solves in place: V_B holds the rhs on entry, the solution on exit.
 template <int NV>
@@ -967,9 +976,9 @@ __device__ __noinline__ void tri_solve(const DevCtx &c, double cc)
     __syncwarp();
 }
 
-// Dispatch: the unrolled 13-row variant needs the padded 416-row layout and the
-// extra factor vector of the FULL layout; everything else takes the generic
-// solver (which also does its own back-substitution).
+// Dispatch: the unrolled 13-row variant needs the padded 416-row layout (FULL
+// layout, 385..416 nodes); everything else takes the generic solver (which also
+// does its own back-substitution).
 template <int NV, bool FULL>
 __device__ __forceinline__ bool tri_is13(const DevCtx &c) { return FULL && c.nxp == 32 * 13; }
 template <int NV, bool FULL>
@@ -980,7 +989,7 @@ __device__ __forceinline__ void tri_factor_warp0(const DevCtx &c, double cc)
 template <int NV, bool FULL>
 __device__ __forceinline__ void tri_solve_warp0(const DevCtx &c, double cc)
 {
-    if (FULL && c.nxp == 32 * 13) tri_solve13<NV>(c); else tri_solve<NV>(c, cc);
+    if (FULL && c.nxp == 32 * 13) tri_solve13<NV>(c, cc); else tri_solve<NV>(c, cc);
 }
 template <int NV, bool FULL>
 __device__ __forceinline__ double tri_x(const DevCtx &c, int i)
@@ -1015,7 +1024,7 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
     }
     __syncthreads();
     const int nxp = c.nxp;
-    double *D = c.dbuf + (size_t)blockIdx.x * 8 * nxp;
+    double *D = HB_GROW(c, G_D);
     const int nx = c.nx;
     HB_FOR_CELLS(p) {
         double col[6], out[6];
@@ -1075,7 +1084,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                                         const double *y_glob, int jac_only = 0)
 {
     // jac_only (test hook): 1 = return after the initial Jacobian, 2 = the same
-    // but starting from the step factors already in V_FAC.
+    // but starting from the step factors already in the G_FAC scratch row.
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     enum { S_F0, S_F1, S_JB, S_JG, S_JR, S_NW };
     enum { GO_NONE, GO_JAC_END, GO_STEP_BEGIN, GO_STEP_RETRY, GO_PREDICT, GO_NEWTON_BEGIN,
@@ -1083,10 +1092,10 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
     const int nx = c.nx, nxp = c.nxp, tid = threadIdx.x;
     const double rtol = c.rtol, atol = c.atol;
     const double newton_tol = fmax(10.0 * HB_EPS / rtol, fmin(0.03, sqrt(rtol)));
-    double *D = c.dbuf + (size_t)blockIdx.x * 8 * nxp, *y = HB_VEC(c, V_Y), *b = HB_VEC(c, V_B);
+    double *D = HB_GROW(c, G_D), *y = HB_VEC(c, V_Y), *b = HB_VEC(c, V_B);
     double *vpsi = HB_VEC(c, V_PSI), *vscl = HB_VEC(c, V_SCL), *vd = HB_VEC(c, V_DD);
     double *fbv = HB_VEC(c, V_TW), *fnv = HB_VEC(c, V_TIP), *ybv = HB_VEC(c, V_TVL),
-           *hv = HB_VEC(c, V_TVR), *fac = HB_VEC(c, V_FAC);
+           *hv = HB_VEC(c, V_TVR), *fac = HB_GROW(c, G_FAC);
     double *jl = HB_VEC(c, V_JL), *jd = HB_VEC(c, V_JD), *ju = HB_VEC(c, V_JU);
     long long *cnt = reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT));
     const Statics S = statics_of<FULL>(c, col);
@@ -1125,7 +1134,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 b[i] = cc * f - vpsi[i] - vd[i];
             }
 #if HB_DUP_PROBE
-            if (c.dbg & 128) { double *s2 = HB_VEC(c, V_SK); for (int i = tid; i < nx; i += NT) s2[i] = cc * b[i] - vpsi[i] - vd[i]; }
+            if (c.dbg & 128) { double *s2 = HB_GROW(c, G_SK); for (int i = tid; i < nx; i += NT) s2[i] = cc * b[i] - vpsi[i] - vd[i]; }
 #endif
             bool converged = false, stop = false;
             if (!__syncthreads_and(finite)) stop = true;
@@ -1133,7 +1142,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 HB_TICK(c, NV, 3);           // residual + barrier
 #if HB_DUP_PROBE
                 if (c.dbg & 3) {             // bit 0: a second solve; bit 1: only its copies and barriers
-                    double *s1 = HB_VEC(c, V_TH), *s2 = HB_VEC(c, V_SK);
+                    double *s1 = HB_GROW(c, G_TH), *s2 = HB_GROW(c, G_SK);
                     for (int i = tid; i < nx; i += NT) s1[i] = b[i];
                     __syncthreads();
                     if ((c.dbg & 1) && tid < 32) tri_solve_warp0<NV, FULL>(c, c_lu);
@@ -1148,7 +1157,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 HB_TICK(c, NV, 4);           // tridiagonal solve + barrier
                 double loc = 0.0;
 #if HB_DUP_PROBE
-                if (c.dbg & 256) { double *s1 = HB_VEC(c, V_TH), *s2 = HB_VEC(c, V_SK);
+                if (c.dbg & 256) { double *s1 = HB_GROW(c, G_TH), *s2 = HB_GROW(c, G_SK);
                     for (int i = tid; i < nx; i += NT) { const double dy = b[i]; const double q = hb_div(dy, vscl[i]); loc += q * q; s1[i] = y[i] + dy; s2[i] = vd[i] + dy; }
                     loc = 0.0; }
 #endif
@@ -1229,7 +1238,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                     if (tid == 0) cnt[K_NSTEPS]++;
                     const bool decide = (n_equal >= order + 1);
 #if HB_DUP_PROBE
-                    if (c.dbg & 1024) { double *s2 = HB_VEC(c, V_SK);
+                    if (c.dbg & 1024) { double *s2 = HB_GROW(c, G_SK);
                         for (int i = tid; i < nx; i += NT) { double a = vd[i] - D[(order + 1) * nxp + i];
                             for (int kk = order; kk >= 0; --kk) a += D[kk * nxp + i] + D[(kk + 1) * nxp + i];
                             s2[i] = a; D[7 * nxp + i] = a; } }
