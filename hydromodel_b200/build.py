@@ -11,6 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hb_capi.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "hb_device.cuh"),
+        os.path.join(HERE, "csrc", "hb_device_impl.cuh"), os.path.join(HERE, "csrc", "hb_kernels.cuh"),
         os.path.join(HERE, "..", "include", "hydrob200.h"),
         os.path.join(HERE, "..", "include", "hb_layout.h")]
 LIB = os.path.join(HERE, "lib", "libhydrob200.so")

@@ -1,0 +1,276 @@
+// hb_kernels.cuh -- the kernels of the path; included by hb_device.cuh once per instance
+// namespace, right after hb_device_impl.cuh.  No include guard on purpose.
+namespace HB_IMPL_NS {
+using namespace hb;
+
+__device__ inline void add_counters(long long *dst, const long long *k, long long windows, bool atomic = true)
+{
+    const long long v[HB_NCOUNTER] = {k[K_NFEV], k[K_NJEV], k[K_NLU], k[K_NSTEPS], k[K_NREJECT],
+                                      k[K_NFAIL], k[K_NRHS], k[K_NNEWTON], windows};
+    for (int i = 0; i < HB_NCOUNTER; ++i) {
+        if (atomic) atomicAdd(reinterpret_cast<unsigned long long *>(dst) + i, (unsigned long long)v[i]);
+        else dst[i] += v[i];
+    }
+}
+
+// Closure on the nodes at the state in V_Y with the noise in V_NR (the
+// diagnostic call of simulation.py:564,623: node k uses n_rnd[k]).
+template <int NT, int NV>
+__device__ inline void nodes_diag(const DevCtx &c, int col, double *th, double *K, double *C, double *kb)
+{
+    const int nx = c.nx;
+    const double *st = c.stat + (size_t)col * HB_NSTATIC * nx;
+    for (int k = threadIdx.x; k < nx; k += NT) {
+        Clos r;
+        closure_cold(HB_XA(c, NV, X_PAR), HB_VEC(c, V_Y)[k], st[(size_t)HB_S_PHI_NODE * nx + k],
+                     st[(size_t)HB_S_KMEAN_NODE * nx + k], st[(size_t)HB_S_COEF_NODE * nx + k],
+                     HB_VEC(c, V_NR)[k], &r);
+        th[k] = r.theta; K[k] = r.K; kb[k] = r.kb;
+        if (C) C[k] = r.C;
+    }
+}
+
+// Diagnostics of one row: estimated water table, lateral flow of the last RHS
+// evaluation (arg_out, quirk Q6) and, on output rows, the closure on the nodes
+// (simulation.py:612-630).  State is in V_Y.
+template <int NT, int NV>
+__device__ inline void write_row(const DevCtx &c, int &parity, int col, int row, int status, bool solved)
+{
+    const int nx = c.nx, tid = threadIdx.x;
+    double *ws = c.wscal + ((size_t)col * c.T + row) * HB_NWSCAL;
+    if (status == 2) {
+        if (tid == 0) { ws[HB_W_WTD_EST] = 0.0; ws[HB_W_LATERAL] = 0.0; ws[HB_W_TRANSP] = 0.0; ws[HB_W_STATUS] = 2.0; }
+        return;
+    }
+    const int wtd_est = find_wtd_nodes<NT, NV>(c, parity, HB_VEC(c, V_Y));
+    if (tid == 0) {
+        ws[HB_W_WTD_EST] = (double)wtd_est;
+        ws[HB_W_LATERAL] = solved ? lateral_flow<NT, NV>(c) : 0.0;
+        ws[HB_W_TRANSP] = solved ? HB_XA(c, NV, X_MISC)[1] : 0.0;
+        ws[HB_W_STATUS] = (double)status;
+    }
+    if (c.fields && c.out_stride > 0 && (row % c.out_stride == 0 || row == c.T - 1)) {
+        const int o = (row % c.out_stride == 0) ? row / c.out_stride : c.n_out - 1;
+        double *f = c.fields + ((size_t)col * c.n_out + o) * HB_NFIELD * nx;
+        for (int k = tid; k < nx; k += NT) f[(size_t)HB_F_PSI * nx + k] = HB_VEC(c, V_Y)[k];
+        nodes_diag<NT, NV>(c, col, f + (size_t)HB_F_THETA * nx, f + (size_t)HB_F_K * nx, nullptr,
+                           f + (size_t)HB_F_KBKG * nx);
+    }
+}
+
+// Work item = (column, chunk of c.chunk consecutive rows).  Tickets are handed
+// out in chunk-major order, so a persistent CTA that finishes early keeps
+// pulling work and the tail of the launch is at most one chunk long (columns
+// differ in cost: step counts, retries).  Chunk j of a column may only start
+// when chunk j-1 is finished; its ticket is lower and therefore already held
+// by a running CTA, so the (rare) wait below cannot deadlock.
+template <int NT, int CPT, int MB, bool FULL>
+__global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
+{
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
+    __shared__ int s_ticket;
+    const int nx = c.nx, tid = threadIdx.x;
+    double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
+    const int n_chunks = (w1 - w0 + c.chunk - 1) / c.chunk;
+    int parity = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(c.queue, 1);
+        __syncthreads();
+        const int ticket = s_ticket;
+        if (ticket >= c.n_cols * n_chunks) break;
+        const int chunk = ticket / c.n_cols, col = ticket % c.n_cols;
+        const int r0 = w0 + chunk * c.chunk, r1 = min(r0 + c.chunk, w1);
+        if (tid == 0 && chunk > 0) {
+            volatile int *dn = c.done + col;
+            while (*dn < chunk) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        bind_column<NT, FULL>(c, col);
+        double *psi_g = c.psi + (size_t)col * nx;
+        double *nb = c.noise_base + (size_t)col * nx;
+        for (int i = tid; i < nx; i += NT) { nr[i] = nb[i]; y[i] = __ldcg(psi_g + i); }
+        bool nr_is_base = true;
+        const int ser = c.series ? c.series[col] : 0;
+        long long windows = 0;
+        __syncthreads();
+        for (int row = r0; row < r1; ++row) {
+            int status = 0;
+            bool solved = false;
+            if (row > 0) {
+                const int wtd = c.wtd_idx[(size_t)ser * c.T + row];
+                if (wtd < 0) status = 2;
+                else {
+                    const double p = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
+                    const bool refresh = (p > 0.5) || (row % 48 == 0);   // simulation.py:599
+                    __syncthreads();
+                    if (refresh) {
+                        if (c.noise_mode == HB_NOISE_TAPE) {
+                            const int slot = __ldcg(c.slot_next + col);          // uniform read
+                            const double *src = c.tape + ((size_t)col * c.n_slots + min(slot, c.n_slots - 1)) * nx;
+                            for (int i = tid; i < nx; i += NT) nr[i] = src[i];
+                            __syncthreads();
+                            if (tid == 0) c.slot_next[col] = slot + 1;
+                        } else {
+                            for (int i = tid; i < nx; i += NT)
+                                nr[i] = philox_normal(c.seed, c.col_offset + col, row, i);
+                        }
+                        nr_is_base = false;
+                    } else if (!nr_is_base) {
+                        for (int i = tid; i < nx; i += NT) nr[i] = __ldcg(nb + i);
+                        nr_is_base = true;
+                    }
+                    __syncthreads();
+                    Args a;
+                    a.precip = p; a.wtd = wtd;
+                    a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
+                    a.atm = c.atm ? c.atm[(size_t)ser * c.T + row] : 0.0;
+                    bool damped = false;
+                    status = solve_window<NT, CPT, FULL>(c, col, a, (double)(row - 1), (double)row, psi_g, damped);
+                    if (damped && nr_is_base)
+                        for (int i = tid; i < nx; i += NT) nb[i] = nr[i];
+                    for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
+                    windows++; solved = true;
+                }
+            }
+            write_row<NT, NV>(c, parity, col, row, status, solved);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            add_counters(c.counters + (size_t)col * HB_NCOUNTER,
+                         reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), windows);
+#if HB_PHASE_TIMING
+            for (int k = 0; k < 15; ++k)
+                atomicAdd(reinterpret_cast<unsigned long long *>(c.phase_cycles) + k,
+                          (unsigned long long)reinterpret_cast<long long *>(HB_XA(c, NV, X_TIME))[k]);
+#endif
+            __threadfence();                   // state, noise, counters before the hand-over
+            atomicExch(c.done + col, chunk + 1);
+        }
+    }
+}
+
+template <int NT, int CPT, int MB, bool FULL>
+__global__ void __launch_bounds__(NT, MB) spinup_kernel(const __grid_constant__ DevCtx c, int max_iter,
+                                                         const double *nrnd0, const double *zwtd0,
+                                                         int *iters_out)
+{
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
+    __shared__ int s_col;
+    const int nx = c.nx, tid = threadIdx.x;
+    double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
+    int parity = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_col = atomicAdd(c.queue, 1);
+        __syncthreads();
+        const int col = s_col;
+        if (col >= c.n_cols) break;
+        bind_column<NT, FULL>(c, col);
+        double *psi_g = c.psi + (size_t)col * nx;
+        for (int i = tid; i < nx; i += NT)
+            nr[i] = nrnd0 ? nrnd0[(size_t)col * nx + i]
+                          : philox_normal(c.seed, c.col_offset + col, -1, i);
+        const int ser = c.series ? c.series[col] : 0;
+        __syncthreads();
+        Args a;
+        a.precip = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T];
+        a.wtd = c.wtd_idx[(size_t)ser * c.T]; a.mode = 2; a.atm = 0.0;
+        const double dz = HB_XA(c, NV, X_PAR)[HB_P_DZ];
+        int it = 0;
+        for (it = 0; it < max_iter; ++it) {
+            bool damped = false;
+            solve_window<NT, CPT, FULL>(c, col, a, 0.0, 1.0, psi_g, damped);
+            const int wtd_est = find_wtd_nodes<NT, NV>(c, parity, y);
+            const double abs_err = fabs(zwtd0[col] - c.x[wtd_est]);
+            double loc = 0.0;
+            for (int i = tid; i < nx; i += NT) { const double dl = y[i] - psi_g[i]; loc += dl * dl; }
+            const double mse = block_sum<NT, NV>(c, parity, loc) / (double)nx;
+            for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
+            if (abs_err <= 2.0 * dz && mse <= 0.01) { it++; break; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            add_counters(c.counters + (size_t)col * HB_NCOUNTER,
+                         reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), it);
+            if (iters_out) iters_out[col] = it;
+        }
+    }
+}
+
+
+
+template <int NT, int CPT, int MB, bool FULL>
+__global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ DevCtx c, HookArgs h)
+{
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
+    const int nx = c.nx, tid = threadIdx.x;
+    bind_column<NT, FULL>(c, h.col);
+    double *io = h.io;
+    double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR), *b = HB_VEC(c, V_B);
+    Args a;
+    a.precip = h.precip; a.wtd = h.wtd; a.mode = h.spinup ? 2 : (h.daylight ? 1 : 0); a.atm = h.atm;
+    int parity = 0;
+    for (int i = tid; i < nx; i += NT) { y[i] = io[i]; nr[i] = io[nx + i]; }
+    __syncthreads();
+    if (h.mode == HK_RHS) {
+        const Statics S = statics_of<FULL>(c, h.col);
+        rhs_eval<NT, CPT, NV>(c, S, h.col, a.precip, a.wtd, a.mode, a.atm, V_B, parity);
+        for (int i = tid; i < nx; i += NT) io[2 * nx + i] = b[i];
+        __syncthreads();
+        if (tid == 0) { io[3 * nx] = lateral_flow<NT, NV>(c); io[3 * nx + 1] = HB_XA(c, NV, X_MISC)[1]; }
+    } else if (h.mode == HK_NODES) {
+        nodes_diag<NT, NV>(c, h.col, io + 2 * nx, io + 3 * nx, io + 4 * nx, io + 5 * nx);
+    } else if (h.mode == HK_JAC) {
+        // the production state machine, stopped right after the initial Jacobian
+        if (!h.first) for (int i = tid; i < nx; i += NT) HB_GROW(c, G_FAC)[i] = io[2 * nx + i];
+        bdf_attempt<NT, CPT, FULL>(c, h.col, a.precip, a.wtd, a.mode, a.atm, 0.0, 1.0, io, h.first ? 1 : 2);
+        for (int i = tid; i < nx; i += NT) {
+            io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
+            io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_GROW(c, G_FAC)[i];
+        }
+    } else if (h.mode == HK_TRI) {
+        for (int i = tid; i < nx; i += NT) {
+            HB_VEC(c, V_JL)[i] = io[2 * nx + i]; HB_VEC(c, V_JD)[i] = io[3 * nx + i];
+            HB_VEC(c, V_JU)[i] = io[4 * nx + i]; b[i] = io[5 * nx + i];
+        }
+        __syncthreads();
+        // factor once, solve; the solve is repeated (same input) to expose cold-code
+        // effects: cycles of repetition r go to io[7*nx + r] (diagnostic)
+        long long t_f0 = clock64();
+        if (tid < 32) {
+            tri_factor_warp0<NV, FULL>(c, h.c);
+        }
+        long long t_f1 = clock64();
+        for (int rep = 0; rep < 4; ++rep) {
+            __syncthreads();
+            for (int i = tid; i < nx; i += NT) b[i] = io[5 * nx + i];
+            __syncthreads();
+            const long long t0 = clock64();
+            if (tid < 32) {
+                tri_solve_warp0<NV, FULL>(c, h.c);
+            }
+            const long long t1 = clock64();
+            if (tid == 0) io[7 * nx + 1 + rep] = (double)(t1 - t0);
+        }
+        if (tid == 0) io[7 * nx] = (double)(t_f1 - t_f0);
+        __syncthreads();
+        for (int i = tid; i < nx; i += NT) io[6 * nx + i] = tri_x<NV, FULL>(c, i);
+    } else if (h.mode == HK_WINDOW) {
+        bool damped = false;
+        const int st = solve_window<NT, CPT, FULL>(c, h.col, a, h.t0, h.t1, io, damped);
+        for (int i = tid; i < nx; i += NT) { io[2 * nx + i] = y[i]; io[nx + i] = nr[i]; }
+        __syncthreads();
+        if (tid == 0) {
+            io[3 * nx] = lateral_flow<NT, NV>(c);
+            io[3 * nx + 1] = HB_XA(c, NV, X_MISC)[1];
+            long long z[HB_NCOUNTER] = {0};
+            add_counters(z, reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), 1, false);
+            for (int k = 0; k < HB_NCOUNTER; ++k) h.stats[k] = z[k];
+            h.stats[HB_NCOUNTER] = st;
+        }
+    }
+}
+
+}  // namespace HB_IMPL_NS

@@ -171,6 +171,16 @@ def test_config1_work_item_order_independence(config1, monkeypatch):
         assert same_bits(out, res, sel=sel) is None, chunk
 
 
+def test_compile_time_and_run_time_layout_instances_agree(config1, monkeypatch):
+    """401-node columns run the instance compiled for the padded vector length 416;
+    the run-time-length instance of the same code must give the same bits."""
+    cols, ic, tape, out = config1
+    sel = list(range(200, 264))
+    monkeypatch.setenv("HB_NO_FIXED", "1")
+    res = run_job(cols, ic, tape=tape, sel=sel)
+    assert same_bits(out, res, sel=sel) is None
+
+
 def test_config1_sample_against_oracle(config1):
     cols, ic, tape, out = config1
     oracle_sample(cols, tape, ic, out, sample=[0, 201, 510], rows=60)
