@@ -40,11 +40,12 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# dram__bytes_read.sum (365.1 MB) + dram__bytes_write.sum (686.1 MB) of run_kernel<256,2,2,true> for
-# (columns, rows, out_stride, nx) below: 2.5x the 413 MB of algorithmic bytes -- the time-sliced
-# scheduler hands state and noise field of a column over through HBM every 16 rows (+150 MB each
-# way) and the L2 writes back difference-table / stack lines; 1.3 GB/s in total, 2e-4 of the HBM peak
-NCU_TRAFFIC = {"workload": (1024, 365, 30, 401), "bytes": 365125888 + 686119424,
+# dram__bytes_read.sum (329.0 MB) + dram__bytes_write.sum (271.4 MB) of run_kernel<256,2,2,true> for
+# (columns, rows, out_stride, nx) below: 1.45x the 413 MB of algorithmic bytes -- the time-sliced
+# scheduler hands state and noise field of a column over through HBM every 16 rows; 0.9 GB/s in
+# total, 1.4e-4 of the HBM peak.  (Before the shared-memory layout was cut to 18 vectors the same
+# launch wrote 686 MB: spill-stack lines evicted from a smaller L1.)
+NCU_TRAFFIC = {"workload": (1024, 365, 30, 401), "bytes": 329000704 + 271376128,
                "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"}
 
 

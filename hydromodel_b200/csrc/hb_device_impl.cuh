@@ -839,6 +839,26 @@ __device__ __forceinline__ double tri_x(const DevCtx &c, int i)
 // ---------------------------------------------------------------------------
 // change_D (SCIPY bdf.py:18-33): D[0..order] <- (R U)^T D[0..order].
 // ---------------------------------------------------------------------------
+template <int NT, int CPT, int Q>
+__device__ __forceinline__ void transform_D(double *D, int nxp, int nx, const double *ru)
+{
+    const int tid = threadIdx.x;
+    HB_FOR_CELLS(p) {
+        double col[Q], out[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) col[j] = D[j * nxp + p];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) acc += ru[j * 6 + i] * col[j];
+            out[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < Q; ++i) D[i * nxp + p] = out[i];
+    }
+}
+
 template <int NT, int CPT, int NV>
 __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
 {
@@ -863,20 +883,12 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
     __syncthreads();
     const int nxp = HB_NXP(c);
     double *D = HB_GROW(c, G_D);
-    const int nx = c.nx;
-    HB_FOR_CELLS(p) {
-        double col[6], out[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) col[j] = (j < q) ? D[j * nxp + p] : 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) if (j < q) acc += ru[j * 6 + i] * col[j];
-            out[i] = acc;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) if (i < q) D[i * nxp + p] = out[i];
+    switch (q) {                           // D[0..order] <- (R U)^T D[0..order], unrolled per order
+    case 2: transform_D<NT, CPT, 2>(D, nxp, c.nx, ru); break;
+    case 3: transform_D<NT, CPT, 3>(D, nxp, c.nx, ru); break;
+    case 4: transform_D<NT, CPT, 4>(D, nxp, c.nx, ru); break;
+    case 5: transform_D<NT, CPT, 5>(D, nxp, c.nx, ru); break;
+    default: transform_D<NT, CPT, 6>(D, nxp, c.nx, ru); break;
     }
 }
 
@@ -1105,8 +1117,13 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                         double em = INFINITY, ep = INFINITY;
                         if (order > 1) em = rms<NT, NV>(c, par_, lm);
                         if (order < HB_MAX_ORDER) ep = rms<NT, NV>(c, par_, lp);
-                        const double fm_ = inv_root(em, order), fe_ = inv_root(error_norm, order + 1),
-                                     fp_ = inv_root(ep, order + 2);
+                        // the three factors are one pow() per warp: lane l % 3 evaluates its own
+                        // argument pair, lanes 0..2 broadcast (same function, same bits; every
+                        // warp used to evaluate all three one after the other)
+                        const int l3 = (tid & 31) % 3;
+                        const double r3 = inv_root((l3 == 0) ? em : (l3 == 1) ? error_norm : ep, order + l3);
+                        const double fm_ = __shfl_sync(HB_FULL, r3, 0), fe_ = __shfl_sync(HB_FULL, r3, 1),
+                                     fp_ = __shfl_sync(HB_FULL, r3, 2);
                         int delta = -1; double best = fm_;
                         if (fe_ > best) { best = fe_; delta = 0; }
                         if (fp_ > best) { best = fp_; delta = 1; }

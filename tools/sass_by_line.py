@@ -1,7 +1,7 @@
 """Static SASS instruction count per CUDA source line range for one device function."""
 import os, re, subprocess, sys, tempfile, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-key = "run_kernelILi256ELi2ELi2ELb1E"; fn = sys.argv[1] if len(sys.argv) > 1 else "bdf_attempt"
+key = "hbf10run_kernelILi256ELi2ELi2ELb1E"; fn = sys.argv[1] if len(sys.argv) > 1 else "bdf_attempt"
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "hydromodel_b200/lib/libhydrob200.so")], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
