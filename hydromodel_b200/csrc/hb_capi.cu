@@ -195,7 +195,8 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     // 385..416 nodes (the reference's 401-node default): pad every vector to
     // 32 x 13 rows so that the tridiagonal solver runs its unrolled variant
     if (nx > 32 * 12 && nx <= 32 * 13 && !getenv("HB_NO_TRI13")) d.nxp = 32 * 13;
-    d.rtol = 1e-3; d.atol = 1e-3;
+    d.rtol = 1e-3; d.atol = 1e-3; d.sqrt_nx = sqrt((double)nx);
+    d.newton_tol = fmax(10.0 * HB_EPS / d.rtol, fmin(0.03, sqrt(d.rtol)));
     ctx->variant = nx <= 448 ? 0 : (nx <= 512 ? 1 : (nx <= 1024 ? 2 : 3));
     if (const char *v = getenv("HB_VARIANT")) {          // tuning experiments
         const int want = atoi(v);
@@ -320,6 +321,7 @@ int hb_set_tolerances(hb_ctx *ctx, double rtol, double atol)
 {
     if (!ctx || !(rtol > 0.0) || !(atol >= 0.0)) return fail("hb_set_tolerances: bad argument");
     ctx->d.rtol = rtol; ctx->d.atol = atol;
+    ctx->d.newton_tol = fmax(10.0 * HB_EPS / rtol, fmin(0.03, sqrt(rtol)));
     return 0;
 }
 

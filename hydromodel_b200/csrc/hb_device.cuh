@@ -55,6 +55,8 @@ struct DevCtx {
     int *done;               // [n_cols] finished window-chunks per column (time-slicing)
     int chunk;               // windows per work item of run_kernel
     int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice
+    double sqrt_nx;          // sqrt((double)nx), the denominator of the RMS norm
+    double newton_tol;       // max(10 eps / rtol, min(0.03, sqrt(rtol)))  (bdf.py:220)
     unsigned long long seed;
     long long col_offset;
 };
@@ -139,7 +141,8 @@ enum {                      // offsets (doubles) inside the small area
     X_CNT = X_WMAX + 16,    // [8 long long] solver counters (thread 0 writes)
     X_SCAN = X_CNT + 8,     // [32] per-warp totals of the block prefix sum (ET)
     X_TIME = X_SCAN + 32,   // [16 long long] phase cycle counters (HB_PHASE_TIMING builds)
-    X_END = X_TIME + 16
+    X_ARGS = X_TIME + 16,   // [8] arguments of the current window: precip, atm, t0, t_bound, wtd, mode
+    X_END = X_ARGS + 8
 };
 enum { K_NFEV = 0, K_NJEV, K_NLU, K_NSTEPS, K_NREJECT, K_NFAIL, K_NRHS, K_NNEWTON };
 

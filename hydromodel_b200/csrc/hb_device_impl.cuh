@@ -21,10 +21,17 @@ __device__ __forceinline__ double block_sum(const DevCtx &c, int &parity, double
     parity ^= 1;
     if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
     __syncthreads();
-    double acc = 0.0;
+    // pairwise tree over the per-warp partial sums (depth log2 instead of a serial
+    // chain of NT/32 dependent additions)
+    constexpr int NW = NT / 32;
+    double t[NW];
 #pragma unroll
-    for (int w = 0; w < NT / 32; ++w) acc += r[w];
-    return acc;
+    for (int w = 0; w < NW; ++w) t[w] = r[w];
+#pragma unroll
+    for (int s = 1; s < NW; s <<= 1)
+#pragma unroll
+        for (int w = 0; w + s < NW; w += 2 * s) t[w] += t[w + s];
+    return t[0];
 }
 
 template <int NT, int NV>
@@ -46,7 +53,7 @@ __device__ __noinline__ int block_max_int(const DevCtx &c, int &parity, int v)
 template <int NT, int NV>
 __device__ __noinline__ double rms(const DevCtx &c, int &parity, double local_sq)
 {
-    return sqrt(block_sum<NT, NV>(c, parity, local_sq)) / sqrt((double)c.nx);
+    return sqrt(block_sum<NT, NV>(c, parity, local_sq)) / c.sqrt_nx;
 }
 
 // rate ** n for the small positive integers of the Newton convergence test
@@ -138,6 +145,21 @@ __device__ __noinline__ void closure_cold(const double *par, double psi, double 
                                           double coef, double e, Clos *out)
 {
     *out = closure(par, psi, phi, kmean, coef, e);
+}
+
+// Arguments of the current window (args_i of simulation.py:591-596 and the t_span of
+// RichardsPDE.solve) in the small shared area.  All threads must call it; it synchronises.
+enum { WA_PRECIP = 0, WA_ATM, WA_T0, WA_TBOUND, WA_WTD, WA_MODE };
+template <int NV>
+__device__ inline void set_window_args(const DevCtx &c, const Args &a, double t0, double t1)
+{
+    __syncthreads();                       // readers of the previous window are done
+    if (threadIdx.x == 0) {
+        double *wa = HB_XA(c, NV, X_ARGS);
+        wa[WA_PRECIP] = a.precip; wa[WA_ATM] = a.atm; wa[WA_T0] = t0; wa[WA_TBOUND] = t1;
+        wa[WA_WTD] = (double)a.wtd; wa[WA_MODE] = (double)a.mode;
+    }
+    __syncthreads();
 }
 
 // Pointers to the static per-cell inputs of the right-hand side: shared memory
@@ -369,9 +391,12 @@ __device__ __noinline__ double evaporation(const double *par, double y0)
 // (each thread writes, and may afterwards read, its own cells).  Contains one
 // __syncthreads(); writes V_CM, V_FM and the small slots WMAX, MISC, LATW.
 template <int NT, int CPT, int NV>
-__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int col, double precip,
-                                         int wtd, int mode, double atm, int out, int &parity)
+__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int col, int out, int &parity)
 {
+    // the row's arguments (precipitation, demand, water-table observation, mode) are read from
+    // shared memory where they are needed instead of living in registers across the integrator loop
+    const double *wa = HB_XA(c, NV, X_ARGS);
+    const int mode = (int)wa[WA_MODE];
     const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *par = HB_XA(c, NV, X_PAR);
     const double *y = HB_VEC(c, V_Y), *nr = HB_VEC(c, V_NR);
@@ -415,7 +440,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
             } else {
                 const double q_inf_max = fmin(2.0 * (phi - cl.theta) * par[HB_P_DZ], cl.kb);
                 double p_left = 0.0;
-                if (ym < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(precip), q_inf_max);
+                if (ym < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(wa[WA_PRECIP]), q_inf_max);
                 if (mode == 1) p_left -= evaporation(par, ym);
                 HB_XA(c, NV, X_MISC)[0] = p_left;
             }
@@ -427,7 +452,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     if (lane == 0) wmax[warp] = deepest;
     __syncthreads();
     HB_TICK(c, NV, 1);                   // closure phase incl. its barrier
-    if (et_on) et_sink<NT, CPT, NV>(c, col, atm, parity);
+    if (et_on) et_sink<NT, CPT, NV>(c, col, wa[WA_ATM], parity);
     else if (tid == 0) HB_XA(c, NV, X_MISC)[1] = 0.0;
     const double *sk = HB_GROW(c, G_SK);
 
@@ -438,7 +463,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
 #pragma unroll
         for (int w = 1; w < NT / 32; ++w) kmax = max(kmax, wmax[w]);
         const int dim_d = nx - 2;
-        const int wtd_obs = min(wtd, dim_d - 1);
+        const int wtd_obs = min((int)wa[WA_WTD], dim_d - 1);
         const int wtd_est = (kmax < 0) ? 0 : min(kmax, dim_d - 1);
         if (wtd_est < wtd_obs) { lo = wtd_est + 1; hi = wtd_obs + 1; }
     }
@@ -929,8 +954,7 @@ __device__ __noinline__ void column_stats(const double *fb, const double *fn, in
 //   V_PSI max |difference|           V_SCL its scale       V_DD "too small" flag
 // ---------------------------------------------------------------------------
 template <int NT, int CPT, bool FULL>
-__device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip, int wtd, int mode,
-                                        double atm, double t0, double t_bound,
+__device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                                         const double *y_glob, int jac_only = 0)
 {
     // jac_only (test hook): 1 = return after the initial Jacobian, 2 = the same
@@ -941,7 +965,8 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
            GO_JAC_BEGIN };
     const int nx = c.nx, nxp = HB_NXP(c), tid = threadIdx.x;
     const double rtol = c.rtol, atol = c.atol;
-    const double newton_tol = fmax(10.0 * HB_EPS / rtol, fmin(0.03, sqrt(rtol)));
+    const double newton_tol = c.newton_tol;
+    const double *wa = HB_XA(c, NV, X_ARGS);          // t0, t_bound of the window (set_window_args)
     double *D = HB_GROW(c, G_D), *y = HB_VEC(c, V_Y), *b = HB_VEC(c, V_B);
     double *vpsi = HB_VEC(c, V_PSI), *vscl = HB_VEC(c, V_SCL), *vd = HB_VEC(c, V_DD);
     double *fbv = HB_VEC(c, V_TW), *fnv = HB_VEC(c, V_TIP), *ybv = HB_VEC(c, V_TVL),
@@ -954,7 +979,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
     // controller state (identical in every thread)
     int state = S_F0, order = 1, n_equal = 0, k_newton = 0, jac_g = 0;
     bool lu_valid = false, current_jac = false, have_old = false, jac_first = true, jac_init = true;
-    double t = t0, t_new = t0, h_abs = 0.0, h_loc = 0.0, min_step = 0.0, cc = 0.0, c_lu = 0.0;
+    double t = wa[WA_T0], t_new = t, h_abs = 0.0, h_loc = 0.0, min_step = 0.0, cc = 0.0, c_lu = 0.0;
     double dy_norm_old = 0.0, d1_init = 0.0, h0_init = 0.0;
 
     __syncthreads();
@@ -969,7 +994,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         if (c.dbg & 8192) { __syncthreads(); __syncthreads(); }
 #endif
         HB_TICK(c, NV, 0);                   // controller glue since the last mark + loop-top barrier
-        rhs_eval<NT, CPT, NV>(c, S, col, precip, wtd, mode, atm, out, par_);
+        rhs_eval<NT, CPT, NV>(c, S, col, out, par_);
         HB_TICK(c, NV, 2);                   // assembly phase
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
         int go = GO_NONE;
@@ -1150,7 +1175,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             const double d0 = rms<NT, NV>(c, par_, l0);
             d1_init = rms<NT, NV>(c, par_, l1);
             const double h0 = (d0 < 1e-5 || d1_init < 1e-5) ? 1e-6 : 0.01 * d0 / d1_init;
-            h0_init = fmin(h0, fabs(t_bound - t0));
+            h0_init = fmin(h0, fabs(wa[WA_TBOUND] - wa[WA_T0]));
             for (int i = tid; i < nx; i += NT) y[i] = D[i] + h0_init * D[nxp + i];
             state = S_F1;
         } else if (state == S_F1) {
@@ -1160,7 +1185,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             const double d2 = rms<NT, NV>(c, par_, l2) / h0_init;
             const double h1 = (d1_init <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0_init * 1e-3)
                                                                  : sqrt(0.01 / fmax(d1_init, d2));
-            h_abs = fmin(fmin(100.0 * h0_init, h1), fabs(t_bound - t0));
+            h_abs = fmin(fmin(100.0 * h0_init, h1), fabs(wa[WA_TBOUND] - wa[WA_T0]));
             // Jacobian at (t0, y0): jac_wrapped's f = fun_single(t0, y0) repeats the
             // evaluation that produced f0 (same inputs, deterministic), so the base
             // value is taken from D[1] = f0 instead of a sixth RHS evaluation
@@ -1267,7 +1292,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
             if (jac_init) {
                 if (jac_only) { __syncthreads(); return 0; }
                 for (int i = tid; i < nx; i += NT) D[nxp + i] = D[nxp + i] * h_abs;   // D[1] = f0 * h
-                order = 1; n_equal = 0; t = t0;
+                order = 1; n_equal = 0; t = wa[WA_T0];
                 go = GO_STEP_BEGIN;
             } else {
                 current_jac = true;
@@ -1276,7 +1301,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
         }
         if (go == GO_STEP_BEGIN) {
             // ---- driver loop / top of _step_impl (ivp.py:659, bdf.py:318-333) --
-            if (t == t_bound) { __syncthreads(); return 0; }
+            if (t == wa[WA_TBOUND]) { __syncthreads(); return 0; }
             min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
             if (h_abs < min_step) {
                 h_loc = min_step;
@@ -1296,8 +1321,8 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col, double precip,
                 return -1;
             }
             t_new = t + h_loc;
-            if (t_new - t_bound > 0.0) {
-                t_new = t_bound;
+            if (t_new - wa[WA_TBOUND] > 0.0) {
+                t_new = wa[WA_TBOUND];
                 change_D<NT, CPT, NV>(c, order, fabs(t_new - t) / h_loc);
                 n_equal = 0; lu_valid = false;
             }
@@ -1353,8 +1378,9 @@ __device__ inline int solve_window(const DevCtx &c, int col, const Args &a, doub
 {
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     int trials = HB_N_TRIALS, status = 0;
+    set_window_args<NV>(c, a, t0, t1);
     while (trials > 0) {
-        status = bdf_attempt<NT, CPT, FULL>(c, col, a.precip, a.wtd, a.mode, a.atm, t0, t1, y_glob);
+        status = bdf_attempt<NT, CPT, FULL>(c, col, y_glob);
         if (status == 0) break;
         for (int i = threadIdx.x; i < c.nx; i += NT) HB_VEC(c, V_NR)[i] *= HB_NOISE_DAMP;
         noise_damped = true;

@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
     __syncthreads();
     if (h.mode == HK_RHS) {
         const Statics S = statics_of<FULL>(c, h.col);
-        rhs_eval<NT, CPT, NV>(c, S, h.col, a.precip, a.wtd, a.mode, a.atm, V_B, parity);
+        set_window_args<NV>(c, a, 0.0, 1.0);
+        rhs_eval<NT, CPT, NV>(c, S, h.col, V_B, parity);
         for (int i = tid; i < nx; i += NT) io[2 * nx + i] = b[i];
         __syncthreads();
         if (tid == 0) { io[3 * nx] = lateral_flow<NT, NV>(c); io[3 * nx + 1] = HB_XA(c, NV, X_MISC)[1]; }
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
     } else if (h.mode == HK_JAC) {
         // the production state machine, stopped right after the initial Jacobian
         if (!h.first) for (int i = tid; i < nx; i += NT) HB_GROW(c, G_FAC)[i] = io[2 * nx + i];
-        bdf_attempt<NT, CPT, FULL>(c, h.col, a.precip, a.wtd, a.mode, a.atm, 0.0, 1.0, io, h.first ? 1 : 2);
+        set_window_args<NV>(c, a, 0.0, 1.0);
+        bdf_attempt<NT, CPT, FULL>(c, h.col, io, h.first ? 1 : 2);
         for (int i = tid; i < nx; i += NT) {
             io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
             io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_GROW(c, G_FAC)[i];
