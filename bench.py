@@ -40,12 +40,12 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# dram__bytes_read.sum (329.0 MB) + dram__bytes_write.sum (271.4 MB) of run_kernel<256,2,2,true> for
-# (columns, rows, out_stride, nx) below: 1.45x the 413 MB of algorithmic bytes -- the time-sliced
-# scheduler hands state and noise field of a column over through HBM every 16 rows; 0.9 GB/s in
-# total, 1.4e-4 of the HBM peak.  (Before the shared-memory layout was cut to 18 vectors the same
+# dram__bytes_read.sum (352.7 MB) + dram__bytes_write.sum (269.5 MB) of run_kernel<256,2,2,true> for
+# (columns, rows, out_stride, nx) below: 1.5x the 413 MB of algorithmic bytes -- the time-sliced
+# scheduler hands state and noise field of a column over through HBM every 16 rows; 1.0 GB/s in
+# total, 1.6e-4 of the HBM peak.  (Before the shared-memory layout was cut to 18 vectors the same
 # launch wrote 686 MB: spill-stack lines evicted from a smaller L1.)
-NCU_TRAFFIC = {"workload": (1024, 365, 30, 401), "bytes": 329000704 + 271376128,
+NCU_TRAFFIC = {"workload": (1024, 365, 30, 401), "bytes": 352691712 + 269521152,
                "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"}
 
 
