@@ -165,7 +165,7 @@ __device__ inline void set_window_args(const DevCtx &c, const Args &a, double t0
 // Pointers to the static per-cell inputs of the right-hand side: shared memory
 // in the FULL layout, global memory (L1/L2) otherwise.
 struct Statics {
-    const double *phi, *km, *cf, *dx, *zx, *xz;
+    const double *phi, *km, *cf;      // (grid metrics dx, zx, xz: read through DevCtx, shared by all columns)
 };
 
 template <bool FULL>
@@ -179,7 +179,6 @@ __device__ __forceinline__ Statics statics_of(const DevCtx &c, int col)
         s.phi = st + (size_t)HB_S_PHI_MID * c.nx; s.km = st + (size_t)HB_S_KMEAN_MID * c.nx;
         s.cf = st + (size_t)HB_S_COEF_MID * c.nx;
     }
-    s.dx = c.dx; s.zx = c.zx; s.xz = c.xz;        // shared by all columns: L1-resident
     return s;
 }
 
@@ -424,7 +423,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
             } else {
                 const double y0 = y[k], y1 = y[k + 1];
                 ym = 0.5 * (y0 + y1);
-                dy = hb_div(y1 - y0, S.dx[k]);
+                dy = hb_div(y1 - y0, c.dx[k]);
                 // noise index is local to the array handed to the closure (quirk Q1)
                 e = nr[k == 0 ? 0 : k - 1];
                 phi = S.phi[k]; km = S.km[k]; cf = S.cf[k];
@@ -490,15 +489,15 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
             //   bottom  (0 + (f_{n-2} - xz*s_{n-2})) / (-xz*C_{n-2})
             double num, den;
             if (i == 0) {
-                const double zx = S.zx[0];
+                const double zx = c.zx[0];
                 den = zx * cm[0];
                 num = HB_XA(c, NV, X_MISC)[0] + (fm[0] + zx * s_i);
             } else if (i < nx - 1) {
-                const double zx = S.zx[i], xz = S.xz[i];
+                const double zx = c.zx[i], xz = c.xz[i];
                 den = zx * cm[i] + xz * cm[i - 1];
                 num = fm[i] - fm[i - 1] + (zx * s_i + xz * s_m);
             } else {
-                const double xz = S.xz[i];
+                const double xz = c.xz[i];
                 den = -xz * cm[i - 1];
                 num = 0.0 + (fm[i - 1] - xz * s_m);
             }
