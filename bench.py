@@ -323,6 +323,7 @@ def main():
     counters = ctx.get_counters()
     clocks = sampler.summary()
     step_ms = float(np.mean(kernel_ms))
+    log(f"[bench] rank {rank}: kernel ms per step {['%.1f' % v for v in kernel_ms]}, clocks {clocks}")
     if dist is not None:
         t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
