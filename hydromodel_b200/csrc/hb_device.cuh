@@ -1,14 +1,20 @@
-// hb_device.cuh -- device code of the batched Richards/BDF solver (sm_100a).
+// hb_device.cuh -- device code of the batched Richards/BDF solver (sm_100a):
+// this file holds the context, the memory layouts and the constants; the device
+// functions (hb_device_impl.cuh) and the kernels (hb_kernels.cuh) are included at
+// the bottom, once per instance namespace (hbr / hbf, see there).
 //
 // Mapping: one CTA integrates one soil column.  Cell i of the column belongs to
-// thread (i % NT); all per-column vectors (BDF difference table, tridiagonal
-// Jacobian and its factors, Newton iterate, noise field, static profiles) live
-// in shared memory in natural order, so neighbour access is a conflict-free
-// shared load and every element-wise update is private to the owning thread.
+// thread (i % NT); the per-column vectors of the Newton iteration (tridiagonal
+// Jacobian and its factors, Newton iterate, RHS scratch, noise field, static
+// profiles) live in shared memory in natural order, so neighbour access is a
+// conflict-free shared load and every element-wise update is private to the
+// owning thread; vectors touched once per step or only by their owner (BDF
+// difference table, step factors, ET vectors) live in a per-CTA global scratch.
 // Scalars of the step controller (h, order, norms ...) are computed redundantly
 // by every thread from block-wide reductions, which keeps control flow
 // CTA-uniform without broadcasts.  The tridiagonal Newton systems are solved by
-// warp 0 with a partition (chunked Thomas) / warp-shuffle PCR hybrid.
+// warp 0 with a partition (chunked Thomas) / PCR hybrid, the back-substitution by
+// all threads.
 //
 // The integrator is written as ONE loop around ONE inlined right-hand-side
 // evaluation (a state machine): the instruction footprint of the hot loop is
