@@ -921,7 +921,7 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
 // maximum among the stored rows j-1..j+1, row 0 when the column is all zero.
 struct ColStat { double dl, dd, du, maxd, scl; };
 
-__device__ __noinline__ void column_stats(const double *fb, const double *fn, int j, int nx,
+__device__ __forceinline__ void column_stats(const double *fb, const double *fn, int j, int nx,
                                           ColStat *o)
 {
     const int lo = j > 0 ? j - 1 : 0, hi = j < nx - 1 ? j + 1 : nx - 1;
@@ -1200,15 +1200,14 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
             for (int rp_ = 0; rp_ < ((state == S_JG) ? HB_DUP(c, 4096) : 1); ++rp_)
             for (int j = tid; j < nx; j += NT) {
                 if (c.grp[j] != jac_g) continue;
+                if (state != S_JG && vd[j] == 0.0) continue;       // retry pass: flagged columns only
+                ColStat cs;                                        // (one inlined call site: stays in registers)
+                column_stats(fbv, fnv, j, nx, &cs);
                 if (state == S_JG) {
-                    ColStat cs;
-                    column_stats(fbv, fnv, j, nx, &cs);
                     jl[j] = cs.dl; jd[j] = cs.dd; ju[j] = cs.du;
                     vpsi[j] = cs.maxd; vscl[j] = cs.scl;
                     vd[j] = (cs.maxd < REJECT * cs.scl) ? 1.0 : 0.0;
-                } else if (vd[j] != 0.0) {
-                    ColStat cs;
-                    column_stats(fbv, fnv, j, nx, &cs);
+                } else {
                     if (vpsi[j] * cs.scl < cs.maxd * vscl[j]) {
                         fac[j] = 10.0 * fac[j];
                         const double ybi = ybv[j];
