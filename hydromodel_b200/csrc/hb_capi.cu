@@ -352,6 +352,7 @@ int hb_set_columns(hb_ctx *ctx, int col0, int ncol, const double *par, const dou
 int hb_set_state(hb_ctx *ctx, int col0, int ncol, const double *psi)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
+    if (!psi) return fail("hb_set_state: null argument");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->d.psi + (size_t)col0 * ctx->d.nx, psi, (size_t)ncol * ctx->d.nx * sizeof(double),
                        cudaMemcpyHostToDevice, ctx->stream));
@@ -362,6 +363,7 @@ int hb_set_state(hb_ctx *ctx, int col0, int ncol, const double *psi)
 int hb_get_state(hb_ctx *ctx, int col0, int ncol, double *psi)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
+    if (!psi) return fail("hb_get_state: null argument");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(psi, ctx->d.psi + (size_t)col0 * ctx->d.nx, (size_t)ncol * ctx->d.nx * sizeof(double),
                        cudaMemcpyDeviceToHost, ctx->stream));
@@ -534,6 +536,7 @@ int hb_get_wscal(hb_ctx *ctx, int col0, int ncol, double *wscal)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
     if (!ctx->forcing_set) return fail("hb_get_wscal: forcing not set");
+    if (!wscal) return fail("hb_get_wscal: null argument");
     const size_t per = (size_t)ctx->d.T * HB_NWSCAL;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(wscal, ctx->d.wscal + col0 * per, ncol * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -546,6 +549,7 @@ int hb_get_fields(hb_ctx *ctx, int col0, int ncol, double *fields)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
     if (!ctx->d.fields) return fail("hb_get_fields: no field output planned (hb_set_output)");
+    if (!fields) return fail("hb_get_fields: null argument");
     const size_t per = (size_t)ctx->d.n_out * HB_NFIELD * ctx->d.nx;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(fields, ctx->d.fields + col0 * per, ncol * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
