@@ -2,16 +2,29 @@
 """
 bench.py -- throughput of the Richards time-stepping hot path.
 
-One "step" = one pass of the window loop of Simulation.run over one ensemble of
-columns (BASELINE.json configs[1]: 1,024 columns per GPU perturbing n / a0 /
-psi_sat around the default input_parameters.json, shared 365-row synthetic daily
-forcing, nx = 401, host noise tape drawn in the reference's RNG order, shared
-spun-up initial state).  Metric: simulated column-years per second
-(1 column-year = 365 windows), whole job over all GPUs.
+Metric: simulated column-years per second (1 column-year = 365 windows = 365 daily
+forcing rows), whole job over all GPUs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
-  python bench.py --impl reference ...                          the CPU restatement
-                                                                of the reference's path
+  --config 2 (default; BASELINE.json configs[2], the configuration the metric is quoted on)
+      65,536-column ensemble (members of SeedSequence(1234): n / a0 / psi_sat / Theta_Max /
+      precipitation multiplier perturbed around the default input_parameters.json), 3,650-row
+      synthetic daily forcing (10 years), nx = 401, vrettas_fung + Stratified, on-device Philox
+      noise, shared spun-up initial state.  STRONG scaling: the 65,536 columns are split over the
+      GPUs (contiguous blocks of global member ids).  One step = the window loop of Simulation.run
+      over the next `--rows-per-step` (48) forcing rows of EVERY column of the job, state carried
+      from step to step (warm-up steps integrate the first rows, the timed steps the following
+      ones), so `--steps 20 --warmup 5` integrates rows 0 .. 1,200 of the 10-year table.
+  --config 1 (BASELINE.json configs[1])
+      1,024 columns PER GPU (weak scaling) perturbing n / a0 / psi_sat, 365-row forcing, host noise
+      tape in the reference's RNG order; one step = the whole year, restarted every step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our CUDA path
+  python bench.py --impl reference ...                           the reference's own CPU
+                                                                 implementation (oracle/_ref, the
+                                                                 unmodified Python package) on all
+                                                                 host cores; falls back to the C
+                                                                 restatement (oracle/hb_oracle.c)
+                                                                 when it cannot be imported
 For N > 1 launch with torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 """
 import argparse
@@ -28,48 +41,55 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from hydromodel_b200 import pack                                   # noqa: E402
+from hydromodel_b200.sharding import column_range                  # noqa: E402
 from hydromodel_b200.synthetic import (synthetic_forcing, default_params,   # noqa: E402
-                                       ensemble_member)
+                                       ensemble_member, ensemble_columns)
 
 SITE = os.path.join(ROOT, "hydromodel_b200", "model_parameters", "site_information.json")
+IC_FILE = os.path.join(ROOT, "hydromodel_b200", "model_parameters", "ic_well10_default.npy")
 ROWS_PER_YEAR = 365
 F_CELL = 470.0          # canonical FP64 flop per midpoint closure+flux
+TOTAL_COLUMNS_CFG2 = 65536
+ROWS_CFG2 = 3650
+PHILOX_SEED = 20240607
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# dram__bytes_read.sum (352.7 MB) + dram__bytes_write.sum (269.5 MB) of run_kernel<256,2,2,true> for
-# (columns, rows, out_stride, nx) below: 1.5x the 413 MB of algorithmic bytes -- the time-sliced
-# scheduler hands state and noise field of a column over through HBM every 16 rows; 1.0 GB/s in
-# total, 1.6e-4 of the HBM peak.  (Before the shared-memory layout was cut to 18 vectors the same
-# launch wrote 686 MB: spill-stack lines evicted from a smaller L1.)
-NCU_TRAFFIC = {"workload": (1024, 365, 30, 401), "bytes": 352691712 + 269521152,
-               "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE run_kernel launch from the committed
+# `ncu --set full` captures, keyed by (config, columns on the GPU, rows in the launch, out_stride).
+# Refreshed whenever the kernel or the workload changes (profiles/README.md says from which file).
+NCU_TRAFFIC = {
+    (1, 1024, 365, 30): {"bytes": 352691712 + 269521152,
+                         "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"},
+}
 
 
 # ----------------------------------------------------------------------------- workload
-def build_workload(n_cols, first_col, n_rows, total_cols):
-    """Pack `n_cols` ensemble members (global ids first_col..) and the shared forcing."""
-    forcing = synthetic_forcing(n_rows)
+def member_kw(config):
+    return {"perturb_theta": config == 2}
+
+
+def build_workload(config, n_cols, first_col, n_rows):
+    """Pack `n_cols` ensemble members (global ids first_col ..) and the shared forcing."""
+    table = synthetic_forcing(n_rows)
     base = default_params(SITE)
-    pars, stats = [], []
-    col = None
-    for c in range(n_cols):
-        p, mult = ensemble_member(base, first_col + c, max(total_cols, 1024))
-        col = pack.pack_column(p, forcing, precip_mult=mult)
-        pars.append(col["par"]); stats.append(col["stat"])
-    default_col = pack.pack_column(base, forcing)
-    return {"x": col["x"], "par": np.stack(pars), "stat": np.stack(stats),
-            "forcing": col["forcing"], "default": default_col}
+    b, cols = ensemble_columns(base, first_col, n_cols, **member_kw(config))
+    ens = pack.pack_ensemble(b, table, cols)
+    return {"x": ens["x"], "par": ens["par"], "stat": ens["stat"], "forcing": ens["forcing"],
+            "default": pack.pack_column(base, table), "table": table, "base": base}
 
 
-def noise_tape(n_cols, first_col, forcing, nx, seed=0):
-    """Standard normals in the reference's draw order for Simulation(seed=c)
-    started from an IC file: run draw, then one draw per refreshing row."""
-    rows = np.arange(forcing["dim_t"])
-    refresh = ((forcing["precipitation_cm"] > 0.5) | (rows % 48 == 0)) & (rows > 0)
+def noise_tape(wl, n_cols, first_col, seed=0):
+    """Standard normals in the reference's draw order for Simulation(seed=c) started from an
+    IC file: run draw, then one draw per refreshing row (the row's precipitation includes the
+    column's multiplier; the tape is as long as the column that refreshes most needs)."""
+    f, nx = wl["forcing"], wl["x"].size
+    rows = np.arange(f["dim_t"])
+    mult = float(wl["par"][:n_cols, pack.P_PRECIP_MULT].max())
+    refresh = ((mult * f["precipitation_cm"] > 0.5) | (rows % 48 == 0)) & (rows > 0) & (f["wtd_idx"] >= 0)
     slots = 1 + int(refresh.sum())
     tape = np.empty((n_cols, slots, nx))
     for c in range(n_cols):
@@ -85,10 +105,10 @@ def algorithmic_flops(counters, nx):
             c[pack.C_NLU] * 24 * nx + (c[pack.C_NSTEPS] + c[pack.C_NREJECT]) * 40 * nx)
 
 
-def algorithmic_bytes(n_cols, n_rows, nx, n_out, slots):
-    """per column-window 32 B scalars + 8*nx per noise refresh +
-    (32*nx + 32) per output row; plus the once-per-column state / statics."""
-    return n_cols * (32.0 * n_rows + 8.0 * nx * slots + (32.0 * nx + 32.0) * n_out +
+def algorithmic_bytes(n_cols, n_rows, nx, n_out_rows, noise_slots):
+    """SURVEY 8(d) per launch: per column-window 32 B of scalars + 8*nx per taped noise refresh +
+    (32*nx + 32) per output row; plus the once-per-launch state / statics of every column."""
+    return n_cols * (32.0 * n_rows + 8.0 * nx * noise_slots + (32.0 * nx + 32.0) * n_out_rows +
                      8.0 * nx * (2 + pack.NSTATIC))
 
 
@@ -127,8 +147,8 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-# ----------------------------------------------------------------------------- CPU arm
-def _cpu_column(args):
+# ----------------------------------------------------------------------------- CPU arms
+def _port_column(args):
     import oracle
     x, grp, par, stat, f, tape, ic, n_rows = args
     t0 = time.perf_counter()
@@ -138,37 +158,80 @@ def _cpu_column(args):
     return time.perf_counter() - t0, stats
 
 
-def cpu_baseline(wl, ic, n_rows, n_sample_cols, threads):
-    """The CPU restatement of the reference's path (oracle/hb_oracle.c: the same
-    algorithm in C, one column per host thread) on a bounded sample."""
+def port_baseline(wl, ic, n_rows, n_sample_cols, threads):
+    """The C restatement of the reference's path (oracle/hb_oracle.c: the same algorithm in C,
+    one column per host thread) on a bounded sample: the first `n_rows` rows of the first
+    `n_sample_cols` members."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
     oracle.lib()
     grp, _ = pack.fd_groups(wl["x"].size)
-    tape = noise_tape(n_sample_cols, 0, wl["forcing"], wl["x"].size)
-    jobs = [(wl["x"], grp, wl["par"][c % wl["par"].shape[0]], wl["stat"][c % wl["par"].shape[0]],
-             wl["forcing"], tape[c], ic, n_rows) for c in range(n_sample_cols)]
+    sub = dict(wl, forcing={k: (v[:n_rows] if isinstance(v, np.ndarray) else v) for k, v in wl["forcing"].items()})
+    sub["forcing"]["dim_t"] = n_rows
+    tape = noise_tape(sub, min(n_sample_cols, wl["par"].shape[0]), 0)
+    n_have = tape.shape[0]
+    jobs = [(wl["x"], grp, wl["par"][c % n_have], wl["stat"][c % n_have], wl["forcing"], tape[c % n_have],
+             ic, n_rows) for c in range(n_sample_cols)]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:       # ctypes releases the GIL
-        res = list(ex.map(_cpu_column, jobs))
+        res = list(ex.map(_port_column, jobs))
     wall = time.perf_counter() - t0
     windows = n_sample_cols * (n_rows - 1)
     stats = np.sum([r[1] for r in res], axis=0)
     return {"value": windows / ROWS_PER_YEAR / wall, "unit": "column-years/s", "cores": threads,
             "kind": "port",
-            "sample": f"{n_sample_cols} columns x {n_rows - 1} windows of the same workload, "
-                      f"{threads} host threads, oracle/hb_oracle.c (C restatement of the reference's "
-                      f"SciPy-BDF path; the reference's own Python runs ~18x slower per core, BASELINE.md)",
+            "sample": f"rows 1..{n_rows - 1} of the first {n_sample_cols} members of the same workload, "
+                      f"{threads} host threads, oracle/hb_oracle.c (C restatement of the reference's SciPy-BDF path)",
             "windows_per_s": windows / wall, "rhs_evals_per_s": float(stats[pack.C_NRHS]) / wall,
             "wall_s": wall}
 
 
-def default_ic(ctx_factory, wl):
+class ReferenceArm:
+    """The reference's own Python implementation (oracle/_ref, unmodified) on all host cores:
+    one `Simulation(seed=c)` per sampled ensemble member in a multiprocessing pool, the shared
+    initial state handed over as IC file, `Simulation.run` over a bounded number of rows."""
+
+    def __init__(self, config, ic, procs):
+        from oracle import ref_runner
+        self.config, self.procs = config, procs
+        self.table = synthetic_forcing(ROWS_CFG2 if config == 2 else ROWS_PER_YEAR)
+        base = default_params(SITE)
+        self.members = []
+        for c in range(max(procs, 16)):
+            p, m = ensemble_member(base, c, **member_kw(config))
+            self.members.append((p, c, m))
+        self.pool = ref_runner.ReferencePool(ic, SITE, procs)
+        self.pool.warm(self.members, self.table)
+
+    def step(self, n_rows=31):
+        wall, windows, cpu_s, _ = self.pool.run(self.members, self.table, n_rows)
+        return {"value": windows / ROWS_PER_YEAR / wall, "unit": "column-years/s", "cores": self.procs,
+                "kind": "reference",
+                "sample": f"rows 1..{n_rows - 1} of the first {len(self.members)} members of the same "
+                          f"workload, unmodified reference Simulation.run (oracle/_ref) in a "
+                          f"{self.procs}-process pool, IC from file, JIT warm-up excluded",
+                "windows_per_s": windows / wall, "wall_s": wall,
+                "per_core_windows_per_s": windows / cpu_s}
+
+    def close(self):
+        self.pool.close()
+
+
+def reference_available():
+    try:
+        from oracle import make_ref, ref_runner
+        make_ref.make()
+        return ref_runner.importable()
+    except Exception as err:                  # noqa: BLE001
+        return False, str(err)
+
+
+def default_ic(device, wl):
     """Shared initial state: device spin-up of the default-parameter column
-    (Simulation.initial_conditions), cached per process.  Untimed setup."""
+    (Simulation.initial_conditions).  Untimed setup."""
     d = wl["default"]
     from hydromodel_b200 import capi
-    ctx = capi.Context(d["x"].size, 1, ctx_factory)
+    ctx = capi.Context(d["x"].size, 1, device)
     grp, ng = pack.fd_groups(d["x"].size)
     ctx.set_grid(d["x"], grp, ng)
     ctx.set_columns(d["par"][None], d["stat"][None])
@@ -182,6 +245,39 @@ def default_ic(ctx_factory, wl):
     return ic, int(iters[0])
 
 
+def time_spinup(device, wl, n_cols, first_col):
+    """Batched spin-up (Simulation.initial_conditions for every column, early stop per column)
+    of the first `n_cols` local members, Philox noise: timed on its own."""
+    import torch
+    from hydromodel_b200 import capi
+    nx = wl["x"].size
+    ctx = capi.Context(nx, n_cols, device)
+    grp, ng = pack.fd_groups(nx)
+    ctx.set_grid(wl["x"], grp, ng)
+    ctx.set_columns(wl["par"][:n_cols], wl["stat"][:n_cols])
+    f = wl["forcing"]
+    ctx.set_forcing(f["precipitation_cm"], f["wtd_idx"], f["daylight"], f["atm"])
+    ctx.set_noise_philox(PHILOX_SEED, first_col)
+    psi0 = np.tile(np.arange(nx) * 5.0, (n_cols, 1))
+    out = None
+    for _ in range(2):                      # first pass warms the code, second is timed
+        ctx.set_state(psi0)
+        ctx.reset_counters()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        iters = ctx.spinup(f["zWtd_cm"][0], None, max_iter=1500)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        cnt = ctx.get_counters().sum(axis=0)
+        out = {"columns": n_cols, "seconds": dt, "iterations_mean": float(iters.mean()),
+               "iterations_max": int(iters.max()), "column_windows_per_s": float(iters.sum()) / dt,
+               "rhs_evals_per_s": float(cnt[pack.C_NRHS]) / dt,
+               "note": "hb_spinup: unit window repeated under SPINUP flags until the water table is "
+                       "within 2 dz and the state stationary (<= 1500 iterations), one launch"}
+    ctx.close()
+    return out
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -189,45 +285,86 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
-    ap.add_argument("--columns", type=int, default=1024, help="columns per GPU")
-    ap.add_argument("--rows", type=int, default=365, help="forcing rows (365 = 1 column-year)")
-    ap.add_argument("--out-stride", type=int, default=30)
+    ap.add_argument("--config", type=int, default=2, choices=(1, 2))
+    ap.add_argument("--columns", type=int, default=None,
+                    help="config 2: columns of the WHOLE job (65,536); config 1: columns per GPU (1,024)")
+    ap.add_argument("--rows", type=int, default=None, help="forcing rows (config 2: 3,650; config 1: 365)")
+    ap.add_argument("--rows-per-step", type=int, default=48, help="config 2: forcing rows integrated per step")
+    ap.add_argument("--out-stride", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spinup", action="store_true", help="skip the separately timed batched spin-up")
+    ap.add_argument("--no-adaptive", action="store_true", help="plain chunk-major schedule")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(a.gpus, world)
-    config = {"workload": "configs[1]: %d-column ensemble per GPU perturbing n/a0/psi_sat "
-                          "(SeedSequence(1234) members), default input_parameters.json, Well 10 "
-                          "(nx=401), vrettas_fung + Stratified, %d synthetic daily rows, shared "
-                          "spun-up IC, host noise tape" % (a.columns, a.rows),
-              "columns_per_gpu": a.columns, "rows": a.rows, "nx": 401,
-              "rows_per_column_year": ROWS_PER_YEAR, "out_stride": a.out_stride,
-              "l2": "256 MiB buffer written between timed steps (L2 flush)",
-              "rtol": 1e-3, "atol": 1e-3}
+    cfg2 = a.config == 2
+    n_rows = a.rows or (ROWS_CFG2 if cfg2 else ROWS_PER_YEAR)
+    out_stride = a.out_stride or (365 if cfg2 else 30)
+    if cfg2:
+        total_cols = a.columns or TOTAL_COLUMNS_CFG2
+        first_col, n_cols = column_range(total_cols, rank, world)
+        if world == 1 and n_gpus > 1:          # a single process asked to act as one of N ranks
+            first_col, n_cols = column_range(total_cols, 0, n_gpus)
+        rps = a.rows_per_step
+        if (a.steps + a.warmup) * rps + 1 > n_rows:
+            raise SystemExit("bench.py: (steps + warmup) * rows-per-step exceeds the forcing table")
+        config = {"workload": "configs[2]: %d-column ensemble (SeedSequence(1234) members: n / a0 / psi_sat / "
+                              "Theta_Max / precipitation multiplier), split over %d GPU(s) (strong scaling), "
+                              "%d-row synthetic daily forcing (10 yr), default input_parameters.json, Well 10 "
+                              "(nx=401), vrettas_fung + Stratified, on-device Philox noise, shared spun-up IC; "
+                              "one step = the next %d forcing rows of every column, state carried across steps"
+                              % (total_cols, n_gpus, n_rows, rps),
+                  "columns_total": total_cols, "columns_per_gpu": total_cols // n_gpus, "rows": n_rows,
+                  "rows_per_step": rps, "nx": 401, "rows_per_column_year": ROWS_PER_YEAR,
+                  "out_stride": out_stride,
+                  "l2": "no flush needed: every step streams its inputs (>= %.1f GB of statics and state per "
+                        "GPU) through HBM, far more than the 126 MB L2" % (total_cols / n_gpus * 401 * 8 * 12 / 1e9),
+                  "rtol": 1e-3, "atol": 1e-3}
+        scaling = "strong"
+    else:
+        n_cols = a.columns or 1024
+        first_col, total_cols, rps = rank * n_cols, n_cols * n_gpus, n_rows
+        config = {"workload": "configs[1]: %d-column ensemble per GPU perturbing n/a0/psi_sat "
+                              "(SeedSequence(1234) members), default input_parameters.json, Well 10 "
+                              "(nx=401), vrettas_fung + Stratified, %d synthetic daily rows, shared "
+                              "spun-up IC, host noise tape; one step = the whole table" % (n_cols, n_rows),
+                  "columns_per_gpu": n_cols, "rows": n_rows, "nx": 401,
+                  "rows_per_column_year": ROWS_PER_YEAR, "out_stride": out_stride,
+                  "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                  "rtol": 1e-3, "atol": 1e-3}
+        scaling = "weak"
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        wl = build_workload(min(a.columns, 64), 0, a.rows, a.columns * n_gpus)
-        ic = np.load(os.path.join(ROOT, "hydromodel_b200", "model_parameters", "ic_well10_default.npy"))
-        n_sample = max(4 * threads, 16)
-        for _ in range(max(a.warmup, 1)):
-            cpu_baseline(wl, ic, min(a.rows, 8), threads, threads)
-        vals = [cpu_baseline(wl, ic, min(a.rows, 121), n_sample, threads) for _ in range(a.steps)]
-        best = max(vals, key=lambda v: v["value"])
+        ic = np.load(IC_FILE)
+        ok, why = reference_available()
+        vals = []
+        if ok:
+            arm = ReferenceArm(a.config, ic, threads)
+            for _ in range(a.warmup):
+                arm.step(3)
+            vals = [arm.step(31) for _ in range(a.steps)]
+            arm.close()
+        else:
+            log(f"[bench] reference not importable ({why}): timing the C restatement instead")
+            wl = build_workload(a.config, 64, 0, n_rows)
+            for _ in range(max(a.warmup, 1)):
+                port_baseline(wl, ic, 8, threads, threads)
+            vals = [port_baseline(wl, ic, 121, max(4 * threads, 16), threads) for _ in range(a.steps)]
         mean = float(np.mean([v["value"] for v in vals]))
-        best = dict(best, value=mean)
+        cb = dict(vals[-1], value=mean)
         print(json.dumps({
             "impl": "reference", "metric": "column_years_per_s", "value": mean,
             "unit": "column-years/s", "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * float(np.mean([v["wall_s"] for v in vals])),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config, "cpu_baseline": best,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "cpu_baseline": cb,
             "e2e": {"value": mean, "unit": "column-years/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
         return
@@ -237,59 +374,71 @@ def main():
     from hydromodel_b200 import capi
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback "
-                         "(use --impl reference for the CPU restatement)")
+                         "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    first_col = rank * a.columns
     t0 = time.time()
-    wl = build_workload(a.columns, first_col, a.rows, a.columns * n_gpus)
+    wl = build_workload(a.config, n_cols, first_col, n_rows)
     nx = wl["x"].size
     f = wl["forcing"]
-    tape = noise_tape(a.columns, first_col, f, nx)
-    ic_path = os.path.join(ROOT, "hydromodel_b200", "model_parameters", "ic_well10_default.npy")
     ic, spin_iters = default_ic(local, wl)
     if rank == 0:
-        log(f"[bench] setup {time.time() - t0:.1f}s; default-column spin-up {spin_iters} iterations")
+        log(f"[bench] setup {time.time() - t0:.1f}s for {n_cols} columns; default-column spin-up {spin_iters} iterations")
         try:
-            ref_ic = np.load(ic_path)
-            log("[bench] max |IC - shipped IC| = %.3e" % np.abs(ic - ref_ic).max())
+            log("[bench] max |IC - shipped IC| = %.3e" % np.abs(ic - np.load(IC_FILE)).max())
         except OSError:
             pass
+    spin = None
+    if rank == 0 and not a.no_spinup:
+        spin = time_spinup(local, wl, min(n_cols, 1024), first_col)
+        log(f"[bench] batched spin-up: {spin}")
 
-    # pinned host staging buffers (e2e copies come from pinned memory)
+    # pinned host staging buffers (e2e copies come from / go to pinned memory)
+    keep = []
+
     def pinned(arr):
         t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
-        return t, t.numpy()
-    keep = []
-    host = {}
-    for name, arr in (("par", wl["par"]), ("stat", wl["stat"]), ("tape", tape),
-                      ("ic", np.tile(ic, (a.columns, 1))), ("precip", f["precipitation_cm"]),
-                      ("atm", f["atm"])):
-        t, v = pinned(arr); keep.append(t); host[name] = v
+        keep.append(t)
+        return t.numpy()
+    tape = None if cfg2 else noise_tape(wl, n_cols, first_col)
+    host = {"par": pinned(wl["par"]), "stat": pinned(wl["stat"]), "state": pinned(np.tile(ic, (n_cols, 1))),
+            "precip": pinned(f["precipitation_cm"]), "atm": pinned(f["atm"])}
+    if tape is not None:
+        host["tape"] = pinned(tape)
+    ic_rows = np.tile(ic, (n_cols, 1))
     grp, ng = pack.fd_groups(nx)
-    ctx = capi.Context(nx, a.columns, local)
+    ctx = capi.Context(nx, n_cols, local)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_grid(wl["x"], grp, ng)
+    if a.no_adaptive:
+        ctx.set_schedule(False)
 
     def upload():
+        """Host -> device copies of one step: statics, forcing, (tape), state."""
         ctx.set_columns(host["par"], host["stat"])
         ctx.set_forcing(host["precip"], f["wtd_idx"], f["daylight"], host["atm"])
-        ctx.set_noise_tape(host["tape"])
-        ctx.set_output(a.out_stride)
-        ctx.set_state(host["ic"])
-
-    def reset_state():
-        ctx.set_noise_tape(host["tape"])       # the run consumes / damps the tape state
-        ctx.set_state(host["ic"])
-        ctx.reset_counters()
+        if tape is not None:
+            ctx.set_noise_tape(host["tape"])
+        ctx.set_output(out_stride)
+        ctx.set_state(host["state"])
 
     upload()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if cfg2:
+        ctx.set_noise_philox(PHILOX_SEED, first_col)
+    n_out = ctx.n_output_rows
+    flush = None if cfg2 else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak_fp64 = ctx.measure_fp64_peak()
+    res = {"wscal": {}, "fields": {}}          # pinned result buffers by row count
+
+    def result_buffer(kind, rows):
+        if rows not in res[kind]:
+            shape = (n_cols, rows, pack.NWSCAL) if kind == "wscal" else (n_cols, rows, pack.NFIELD, nx)
+            res[kind][rows] = pinned(np.empty(shape))
+        return res[kind][rows]
 
     def barrier():
         torch.cuda.synchronize()
@@ -297,130 +446,195 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- kernel-only timing: inputs resident in HBM -------------------------------
-    for _ in range(a.warmup):
-        reset_state(); flush.fill_(1)
-        with torch.cuda.stream(stream):
-            ctx.run(0, a.rows)
-        stream.synchronize()
-    sampler = ClockSampler(local); sampler.start()
-    launches0 = ctx.launch_count
-    kernel_ms = []
-    barrier()
-    wall0 = time.perf_counter()
-    for _ in range(a.steps):
-        reset_state(); flush.fill_(1); torch.cuda.synchronize()
+    def out_rows_of(r0, r1):
+        """Output-row indices [o0, o1) of the fields written for forcing rows [r0, r1)."""
+        o0 = (r0 + out_stride - 1) // out_stride
+        o1 = (r1 - 1) // out_stride + 1
+        if r1 == n_rows and (n_rows - 1) % out_stride:
+            o1 = n_out
+        return o0, max(o0, o1)
+
+    def one_step(r0, r1, timed):
+        """One step end to end: inputs up, window loop on the device, results down.  Returns
+        (wall seconds, kernel milliseconds from CUDA events on the launch stream)."""
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        upload()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
-            ctx.run(0, a.rows)
+            ctx.run(r0, r1)
             e1.record(stream)
-        e1.synchronize()
-        kernel_ms.append(e0.elapsed_time(e1))
-    barrier()
-    wall_kernel_loop = time.perf_counter() - wall0
-    launches = ctx.launch_count - launches0
-    counters = ctx.get_counters()
-    clocks = sampler.summary()
-    step_ms = float(np.mean(kernel_ms))
-    log(f"[bench] rank {rank}: kernel ms per step {['%.1f' % v for v in kernel_ms]}, clocks {clocks}")
-    if dist is not None:
-        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
-    windows = a.columns * (a.rows - 1)
-    value = n_gpus * windows / ROWS_PER_YEAR / (step_ms * 1e-3)
-
-    # ---- end to end through the C-ABI with host buffers ---------------------------
-    n_out = ctx.n_output_rows
-    h2d = sum(host[k].nbytes for k in ("par", "stat", "tape", "ic", "precip", "atm")) + \
-        2 * 4 * a.rows
-    d2h = a.columns * (a.rows * pack.NWSCAL * 8 + n_out * pack.NFIELD * nx * 8 + nx * 8)
-    e2e_s = []
-    res = {}                                   # pinned host buffers the results are read into
-    for name, shape in (("wscal", (a.columns, a.rows, pack.NWSCAL)),
-                        ("fields", (a.columns, n_out, pack.NFIELD, nx)), ("state", (a.columns, nx))):
-        t, v = pinned(np.empty(shape)); keep.append(t); res[name] = v
-    for it in range(2 + a.steps):
-        barrier()
-        t0 = time.perf_counter()
-        upload()
-        with torch.cuda.stream(stream):
-            ctx.run(0, a.rows)
-        wscal = ctx.get_wscal(out=res["wscal"])
-        fields = ctx.get_fields(out=res["fields"])
-        psi_end = ctx.get_state(out=res["state"])
+        ctx.get_wscal(rows=(r0, r1), out=result_buffer("wscal", r1 - r0))
+        o0, o1 = out_rows_of(r0, r1)
+        if o1 > o0:
+            ctx.get_fields(out_rows=(o0, o1), out=result_buffer("fields", o1 - o0))
+        ctx.get_state(out=host["state"])
         torch.cuda.synchronize()
-        if it >= 2:
-            e2e_s.append(time.perf_counter() - t0)
-    e2e_step = float(np.mean(e2e_s))
+        wall = time.perf_counter() - t_a
+        return wall, e0.elapsed_time(e1), o1 - o0
+
+    # ---- the timed loop ---------------------------------------------------------------------
+    # config 2: every step uploads its inputs, integrates the next rows and reads its results
+    #           back, so ONE loop gives both numbers: `value` from the CUDA events around the
+    #           kernel launches, `e2e` from the wall clock around whole steps.
+    # config 1: kernel-only loop with resident inputs first (L2 flushed between steps), then the
+    #           end-to-end loop -- every step restarts the year from the shared IC.
+    walls, kernel_ms, fields_rows = [], [], []
+    if cfg2:
+        with torch.cuda.stream(stream):
+            ctx.run(0, 1)                          # row 0: initial diagnostics only (untimed setup)
+        ctx.sync()
+        result_buffer("wscal", rps); result_buffer("fields", 1)
+        row = 1
+        for _ in range(a.warmup):
+            one_step(row, row + rps, False)
+            row += rps
+        ctx.reset_counters()
+        sampler = ClockSampler(local); sampler.start()
+        launches0 = ctx.launch_count
+        barrier()
+        for _ in range(a.steps):
+            w, k, nf = one_step(row, row + rps, True)
+            walls.append(w); kernel_ms.append(k); fields_rows.append(nf)
+            row += rps
+        barrier()
+        launches = ctx.launch_count - launches0
+        counters = ctx.get_counters()
+        clocks = sampler.summary()
+        windows_per_step = n_cols * rps
+    else:
+        def reset_state():
+            ctx.set_noise_tape(host["tape"])       # the run consumes / damps the tape state
+            ctx.set_state(ic_rows)
+            ctx.reset_counters()
+        for _ in range(a.warmup):
+            reset_state(); flush.fill_(1)
+            with torch.cuda.stream(stream):
+                ctx.run(0, n_rows)
+            stream.synchronize()
+        sampler = ClockSampler(local); sampler.start()
+        launches0 = ctx.launch_count
+        barrier()
+        for _ in range(a.steps):
+            reset_state(); flush.fill_(1); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                ctx.run(0, n_rows)
+                e1.record(stream)
+            e1.synchronize()
+            kernel_ms.append(e0.elapsed_time(e1))
+        barrier()
+        launches = ctx.launch_count - launches0
+        counters = ctx.get_counters()
+        clocks = sampler.summary()
+        for it in range(2 + a.steps):
+            barrier()
+            host["state"][:] = ic_rows
+            w, _, nf = one_step(0, n_rows, True)
+            if it >= 2:
+                walls.append(w); fields_rows.append(nf)
+        windows_per_step = n_cols * (n_rows - 1)
+
+    kernel_s = float(np.sum(kernel_ms)) * 1e-3
+    e2e_s = float(np.sum(walls))
+    log(f"[bench] rank {rank}: kernel ms per step {['%.1f' % v for v in kernel_ms]}, "
+        f"e2e ms per step {['%.1f' % (1e3 * v) for v in walls]}, clocks {clocks}")
+    per_rank_kernel_s = [kernel_s]
     if dist is not None:
-        t = torch.tensor([e2e_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_step = float(t.item())
-    e2e_value = n_gpus * windows / ROWS_PER_YEAR / e2e_step
+        t = torch.tensor([kernel_s, e2e_s], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank_kernel_s = [float(g[0].item()) for g in gathered]
+        kernel_s = max(per_rank_kernel_s)
+        e2e_s = max(float(g[1].item()) for g in gathered)
+    job_windows = (total_cols * rps if cfg2 else n_gpus * windows_per_step) * a.steps
+    value = job_windows / ROWS_PER_YEAR / kernel_s
+    e2e_value = job_windows / ROWS_PER_YEAR / e2e_s
+    step_ms = 1e3 * kernel_s / a.steps
+
+    h2d = sum(host[k].nbytes for k in host) + 2 * 4 * n_rows
+    if cfg2:
+        d2h = n_cols * (rps * pack.NWSCAL * 8 + nx * 8) + int(np.mean(fields_rows) * n_cols * pack.NFIELD * nx * 8)
+    else:
+        d2h = n_cols * (n_rows * pack.NWSCAL * 8 + n_out * pack.NFIELD * nx * 8 + nx * 8)
 
     # ---- ensemble statistics: the one collective of this path (outside the timing) --
-    mom = torch.zeros(2, a.rows, dtype=torch.float64, device="cuda")
+    mom = torch.zeros(3, n_rows, dtype=torch.float64, device="cuda")
+    th = torch.zeros(2, n_out, nx, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    ctx.wtd_moments_dev(mom[0].data_ptr(), mom[1].data_ptr())
+    ctx.moments_dev(mom[0].data_ptr(), mom[1].data_ptr(), mom[2].data_ptr(), th[0].data_ptr(), th[1].data_ptr())
     ctx.sync()
     if dist is not None:
         dist.all_reduce(mom)
-    wtd_mean_last = float(mom[0, -1].item()) / (a.columns * n_gpus)
+        dist.all_reduce(th)
+    last_row = (a.warmup + a.steps) * rps if cfg2 else n_rows - 1     # last row integrated
+    wtd_mean_last = float(mom[1, last_row].item()) / max(float(mom[0, last_row].item()), 1.0)
+    theta_mean_ic = float(th[0, 0].mean().item()) / (total_cols if cfg2 else n_cols * n_gpus)
 
     # ---- roofline ------------------------------------------------------------------
-    flops = algorithmic_flops(counters, nx)
-    slots = tape.shape[1]
-    abytes = algorithmic_bytes(a.columns, a.rows, nx, n_out, slots)
+    flops = algorithmic_flops(counters, nx) / a.steps          # per launch (one launch per step)
+    slots = 0 if tape is None else tape.shape[1]
+    abytes = algorithmic_bytes(n_cols, rps, nx, float(np.mean(fields_rows)) if cfg2 else n_out, slots)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach_tf = flops / (step_ms * 1e-3) / 1e12
-    # DRAM bytes of one run_kernel launch from the committed `ncu --set full` capture of this
-    # very workload (dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
-    traffic, traffic_src = None, None
-    if (a.columns, a.rows, a.out_stride, nx) == NCU_TRAFFIC["workload"]:
-        traffic, traffic_src = NCU_TRAFFIC["bytes"], NCU_TRAFFIC["source"]
-    ach_gbs = abytes / (step_ms * 1e-3) / 1e9
+    own_launch_s = float(np.sum(kernel_ms)) * 1e-3 / a.steps    # this rank's launches
+    ach_tf = flops / own_launch_s / 1e12
+    tr = NCU_TRAFFIC.get((a.config, n_cols, rps, out_stride))
+    ach_gbs = abytes / own_launch_s / 1e9
     csum = counters.sum(axis=0).astype(float)
+    nwin = max(csum[pack.C_NWINDOWS], 1.0)
     result = {
         "metric": "column_years_per_s", "value": value, "unit": "column-years/s",
         "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
-        "windows_per_s": n_gpus * windows / (step_ms * 1e-3),
-        "rhs_evals_per_s": n_gpus * csum[pack.C_NRHS] / (step_ms * 1e-3),
-        "per_window": {"nfev": csum[pack.C_NFEV] / csum[pack.C_NWINDOWS],
-                       "njev": csum[pack.C_NJEV] / csum[pack.C_NWINDOWS],
-                       "nlu": csum[pack.C_NLU] / csum[pack.C_NWINDOWS],
-                       "steps": csum[pack.C_NSTEPS] / csum[pack.C_NWINDOWS],
-                       "rhs": csum[pack.C_NRHS] / csum[pack.C_NWINDOWS],
-                       "failed_attempts": csum[pack.C_NFAIL]},
+        "windows_per_s": job_windows / kernel_s,
+        "rhs_evals_per_s": n_gpus * csum[pack.C_NRHS] / (float(np.sum(kernel_ms)) * 1e-3),
+        "per_window": {"nfev": csum[pack.C_NFEV] / nwin, "njev": csum[pack.C_NJEV] / nwin,
+                       "nlu": csum[pack.C_NLU] / nwin, "steps": csum[pack.C_NSTEPS] / nwin,
+                       "rhs": csum[pack.C_NRHS] / nwin, "failed_attempts": csum[pack.C_NFAIL]},
         "e2e": {"value": e2e_value, "unit": "column-years/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_step},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / a.steps,
+                "note": "wall clock around whole steps through the C-ABI with pinned host buffers: statics, "
+                        "forcing, state up; per-row scalars, output fields, state down"},
         "gpu_launches": int(launches),
+        "per_rank_kernel_ms_per_step": [1e3 * v / a.steps for v in per_rank_kernel_s],
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_fp64, "unit": "TFLOP/s",
-                     "frac": ach_tf / peak_fp64, "traffic": traffic,
-                     "traffic_unit": "DRAM bytes per launch (read + write)", "traffic_source": traffic_src,
+                     "frac": ach_tf / peak_fp64, "traffic": tr["bytes"] if tr else None,
+                     "traffic_unit": "DRAM bytes per launch (read + write)",
+                     "traffic_source": tr["source"] if tr else None,
                      "peak_source": "hb_measure_fp64_peak: register-resident DFMA loop measured in "
                                     "this run (MEASURED_PEAKS.json has no FP64 figure)",
-                     "flops_per_launch": flops,
+                     "flops_per_launch": flops, "kernel": "run_kernel<256,2,2,true>",
                      "note": "algorithmic FP64 flop of SURVEY 8(d) from the kernel's own counters; "
                              "the path is an SMEM-resident FP64 solver, neither HBM- nor tensor-bound"},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "bytes_per_launch": abytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
-        "ensemble": {"wtd_node_mean_last_row": wtd_mean_last,
-                     "collective": "all_reduce(sum) of WTD moments, NCCL" if dist is not None else "none (1 GPU)"},
+        "ensemble": {"wtd_node_mean_last_row": wtd_mean_last, "theta_mean_initial": theta_mean_ic,
+                     "collective": "all_reduce(sum) of WTD and theta moments, NCCL" if dist is not None else "none (1 GPU)"},
     }
-    if rank == 0 and not a.no_cpu_baseline:
+    if spin is not None:
+        result["spinup"] = spin
+    if rank == 0 and not a.no_cpu_baseline and n_gpus == 1:
         threads = os.cpu_count() or 1
-        cb = cpu_baseline(wl, ic, min(a.rows, 121), max(4 * threads, 16), threads)
+        port = port_baseline(wl, ic, 121, max(4 * threads, 16), threads)
+        ok, why = reference_available()
+        if ok:
+            arm = ReferenceArm(a.config, ic, threads)
+            cb = arm.step(31)
+            arm.close()
+            cb["port_value"] = port["value"]
+            cb["port_note"] = port["sample"]
+        else:
+            cb = dict(port, note=f"reference not importable here ({why})")
         result["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(result))

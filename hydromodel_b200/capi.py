@@ -41,11 +41,15 @@ EXPORTS = {
     "hb_n_output_rows": (ct.c_int, [ct.c_void_p]),
     "hb_spinup": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, _I]),
     "hb_run": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
+    "hb_set_schedule": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "hb_get_wscal": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, _D]),
+    "hb_get_wscal_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, _D]),
     "hb_get_fields": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, _D]),
+    "hb_get_fields_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, _D]),
     "hb_get_counters": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, _L]),
     "hb_reset_counters": (ct.c_int, [ct.c_void_p]),
-    "hb_wtd_moments_dev": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p]),
+    "hb_moments_dev": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p,
+                                  ct.c_void_p]),
     "hb_launch_count": (ct.c_int64, [ct.c_void_p]),
     "hb_measure_fp64_peak": (ct.c_double, [ct.c_void_p]),
     "hb_get_phase_cycles": (ct.c_int, [ct.c_void_p, _L]),
@@ -55,6 +59,8 @@ EXPORTS = {
     "hb_num_jac": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, ct.c_double, ct.c_int, ct.c_int,
                               ct.c_int, _D, _D, _D, _D, _D]),
     "hb_tri_solve": (ct.c_int, [ct.c_void_p, _D, _D, _D, ct.c_double, _D, _D]),
+    "hb_find_wtd": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _I]),
+    "hb_philox_normals": (ct.c_int, [ct.c_void_p, ct.c_uint64, ct.c_int64, ct.c_int, ct.c_int, _D]),
     "hb_solve_window": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double, ct.c_double, _D, _D,
                                    ct.c_double, ct.c_int, ct.c_int, ct.c_int, ct.c_double, _D, _L,
                                    _D, _D, ct.POINTER(ct.c_int)]),
@@ -235,16 +241,23 @@ class Context:
     def run(self, w0=0, w1=None):
         self._ck(self.lib.hb_run(self._h, int(w0), int(self.T if w1 is None else w1)))
 
-    def get_wscal(self, col0=0, ncol=None, out=None):
+    def set_schedule(self, adaptive=True):
+        self._ck(self.lib.hb_set_schedule(self._h, int(bool(adaptive))))
+
+    def get_wscal(self, col0=0, ncol=None, out=None, rows=None):
+        """Per-row scalars [ncol][T][NWSCAL]; ``rows=(row0, row1)`` reads that slice only."""
         ncol = self.n_cols - col0 if ncol is None else ncol
-        out = self._out(out, (ncol, self.T, NWSCAL))
-        self._ck(self.lib.hb_get_wscal(self._h, col0, ncol, _d(out)))
+        r0, r1 = (0, self.T) if rows is None else (int(rows[0]), int(rows[1]))
+        out = self._out(out, (ncol, r1 - r0, NWSCAL))
+        self._ck(self.lib.hb_get_wscal_rows(self._h, col0, ncol, r0, r1 - r0, _d(out)))
         return out
 
-    def get_fields(self, col0=0, ncol=None, out=None):
+    def get_fields(self, col0=0, ncol=None, out=None, out_rows=None):
+        """Fields [ncol][n_out][NFIELD][nx]; ``out_rows=(o0, o1)`` reads those output rows only."""
         ncol = self.n_cols - col0 if ncol is None else ncol
-        out = self._out(out, (ncol, self.n_output_rows, NFIELD, self.nx))
-        self._ck(self.lib.hb_get_fields(self._h, col0, ncol, _d(out)))
+        o0, o1 = (0, self.n_output_rows) if out_rows is None else (int(out_rows[0]), int(out_rows[1]))
+        out = self._out(out, (ncol, o1 - o0, NFIELD, self.nx))
+        self._ck(self.lib.hb_get_fields_rows(self._h, col0, ncol, o0, o1 - o0, _d(out)))
         return out
 
     def get_counters(self, col0=0, ncol=None):
@@ -256,8 +269,13 @@ class Context:
     def reset_counters(self):
         self._ck(self.lib.hb_reset_counters(self._h))
 
-    def wtd_moments_dev(self, sum_ptr, sumsq_ptr):
-        self._ck(self.lib.hb_wtd_moments_dev(self._h, ct.c_void_p(sum_ptr), ct.c_void_p(sumsq_ptr)))
+    def moments_dev(self, count_ptr, wtd_sum_ptr, wtd_sumsq_ptr, theta_sum_ptr=None, theta_sumsq_ptr=None):
+        """Ensemble moments into DEVICE buffers (raw pointers): count / sum / sum of squares of
+        the water-table node index per row [T], optionally sum / sum of squares of theta
+        [n_out][nx]."""
+        self._ck(self.lib.hb_moments_dev(self._h, ct.c_void_p(count_ptr), ct.c_void_p(wtd_sum_ptr),
+                                         ct.c_void_p(wtd_sumsq_ptr), ct.c_void_p(theta_sum_ptr),
+                                         ct.c_void_p(theta_sumsq_ptr)))
 
     @property
     def launch_count(self):
@@ -309,6 +327,19 @@ class Context:
         x = np.empty(self.nx)
         self._ck(self.lib.hb_tri_solve(self._h, _d(dl), _d(d), _d(du), float(c), _d(b), _d(x)))
         return x
+
+    def find_wtd(self, col, psi):
+        psi = _f64(psi)
+        assert psi.size == self.nx
+        w = np.zeros(1, dtype=np.int32)
+        self._ck(self.lib.hb_find_wtd(self._h, int(col), _d(psi), _i(w)))
+        return int(w[0])
+
+    def philox_normals(self, seed, global_column, window, n=None):
+        out = np.empty(self.nx if n is None else int(n))
+        self._ck(self.lib.hb_philox_normals(self._h, int(seed), int(global_column), int(window),
+                                            out.size, _d(out)))
+        return out
 
     def solve_window(self, col, t0, t1, y0, nrnd, precip, wtd, daylight=0, spinup=0, atm=0.0):
         """Returns (y_end, stats dict, status, lateral_flow); ``nrnd`` (float64,

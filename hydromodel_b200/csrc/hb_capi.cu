@@ -26,7 +26,7 @@ struct HookArgs {
     double *io;          // device scratch: [8][nx]
     long long *stats;    // [HB_NCOUNTER + 2]
 };
-enum { HK_RHS = 0, HK_NODES, HK_JAC, HK_TRI, HK_WINDOW };
+enum { HK_RHS = 0, HK_NODES, HK_JAC, HK_TRI, HK_WINDOW, HK_WTD };
 #include "hb_device.cuh"
 
 using namespace hb;
@@ -39,6 +39,13 @@ __global__ void philox_base_kernel(DevCtx c)
         const int col = (int)(g / c.nx), i = (int)(g % c.nx);
         c.noise_base[g] = hbr::philox_normal(c.seed, c.col_offset + col, 0, i);
     }
+}
+
+// Test hook: the standard normals run_kernel / spinup_kernel draw for (column, window).
+__global__ void philox_probe_kernel(unsigned long long seed, long long column, int window, int n, double *out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = hbr::philox_normal(seed, column, window, i);
 }
 
 // Register-resident DFMA loop: the FP64 roofline denominator (MEASURED_PEAKS.json
@@ -55,16 +62,98 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
-__global__ void moments_kernel(DevCtx c, double *sum, double *sumsq)
+// Ensemble statistics, two passes so that the sums do not depend on the schedule:
+// every thread owns one element e (a row, or a (output row, node) pair) and adds up
+// a slice of the columns -- neighbouring threads read neighbouring addresses -- into
+// part[slice][3][M]; moments_final_kernel adds the slices in a fixed order.
+// WTD: element = row, value = estimated water-table node index, skipped rows
+// (status 2) do not count.  THETA: element = (output row, node), value = theta.
+template <bool THETA>
+__global__ void __launch_bounds__(256) moments_partial_kernel(DevCtx c, int M, int cols_per_slice, double *part)
 {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= c.T) return;
-    double s = 0.0, q = 0.0;
-    for (int col = 0; col < c.n_cols; ++col) {
-        const double *ws = c.wscal + ((size_t)col * c.T + row) * HB_NWSCAL;
-        if (ws[HB_W_STATUS] != 2.0) { const double v = ws[HB_W_WTD_EST]; s += v; q += v * v; }
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M) return;
+    const int c0 = blockIdx.y * cols_per_slice, c1 = min(c0 + cols_per_slice, c.n_cols);
+    double n = 0.0, s = 0.0, q = 0.0;
+    if (THETA) {
+        const int o = e / c.nx, k = e - o * c.nx;
+        const size_t per_col = (size_t)c.n_out * HB_NFIELD * c.nx;
+        const double *f = c.fields + ((size_t)o * HB_NFIELD + HB_F_THETA) * c.nx + k;
+        for (int col = c0; col < c1; ++col) { const double v = f[col * per_col]; n += 1.0; s += v; q += v * v; }
+    } else {
+        for (int col = c0; col < c1; ++col) {
+            const double2 *ws = reinterpret_cast<const double2 *>(c.wscal + ((size_t)col * c.T + e) * HB_NWSCAL);
+            const double2 a = ws[0], b = ws[1];          // (wtd_est, lateral), (transp, status)
+            if (b.y != 2.0) { n += 1.0; s += a.x; q += a.x * a.x; }
+        }
     }
-    sum[row] = s; sumsq[row] = q;
+    double *dst = part + (size_t)blockIdx.y * 3 * M;
+    dst[e] = n; dst[M + e] = s; dst[2 * (size_t)M + e] = q;
+}
+
+__global__ void __launch_bounds__(256) moments_final_kernel(const double *part, int M, int n_slices, double *count,
+                                                            double *sum, double *sumsq)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M) return;
+    double n = 0.0, s = 0.0, q = 0.0;
+    for (int k = 0; k < n_slices; ++k) {
+        const double *src = part + (size_t)k * 3 * M;
+        n += src[e]; s += src[M + e]; q += src[2 * (size_t)M + e];
+    }
+    if (count) count[e] = n;
+    sum[e] = s; sumsq[e] = q;
+}
+
+// Launch plan of run_kernel from the cost (RHS evaluations) each column had in the
+// previous launch: columns above `factor` x the mean go first and run unpaced
+// ("hot"), the others follow in chunk-major order.  One CTA.  Without a history
+// (all costs zero) the plan is the identity with no hot column.
+__global__ void __launch_bounds__(1024) plan_kernel(const DevCtx c, int cap)
+{
+    __shared__ double s_part[32];
+    __shared__ double s_mean;
+    __shared__ int s_cnt, s_hot, s_reg;
+    const int tid = threadIdx.x, n = c.n_cols;
+    double loc = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) loc += (double)c.cost[i];
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(HB_FULL, loc, o);
+    if ((tid & 31) == 0) s_part[tid >> 5] = loc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+        s_mean = t / (double)n;
+    }
+    __syncthreads();
+    const double mean = s_mean;
+    double thr = 1.5 * mean;
+    for (int it = 0; it < 12; ++it) {          // raise the bar until the hot set fits `cap`
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        int m = 0;
+        for (int i = tid; i < n; i += blockDim.x) m += ((double)c.cost[i] > thr);
+        if (m) atomicAdd(&s_cnt, m);
+        __syncthreads();
+        const int cnt = s_cnt;
+        __syncthreads();
+        if (cnt <= cap) break;
+        thr *= 1.5;
+    }
+    if (!(mean > 0.0)) thr = INFINITY;
+    if (tid == 0) { s_hot = 0; s_reg = 0; }
+    __syncthreads();
+    // two passes keep the order of both lists deterministic only up to the atomics; the
+    // results of the run do not depend on the order (columns are independent)
+    for (int i = tid; i < n; i += blockDim.x)
+        if ((double)c.cost[i] > thr) c.order[atomicAdd(&s_hot, 1)] = i;
+    __syncthreads();
+    const int n_hot = s_hot;
+    for (int i = tid; i < n; i += blockDim.x)
+        if (!((double)c.cost[i] > thr)) c.order[n_hot + atomicAdd(&s_reg, 1)] = i;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) c.cost[i] = 0;
+    if (tid == 0) *c.n_hot = n_hot;
 }
 
 // ==================================================================================
@@ -85,7 +174,7 @@ struct hb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<void *> allocs;
     struct SlotT { void *p = nullptr; size_t bytes = 0; };
-    SlotT s_precip, s_atm, s_wtd, s_day, s_series, s_wscal, s_fields, s_tape, s_nr0, s_zw, s_it;
+    SlotT s_precip, s_atm, s_wtd, s_day, s_series, s_wscal, s_fields, s_tape, s_nr0, s_zw, s_it, s_mom;
     double *hook_io = nullptr;
     long long *hook_stats = nullptr;
     int64_t launches = 0;
@@ -97,6 +186,10 @@ struct hb_ctx {
     bool fixed = false;     // the compile-time nxp = 416 instance (namespace hbf) applies
     size_t smem_bytes = 0;
     int blocks_per_sm = 1;
+    int wscal_T = 0;        // table length the per-row result buffer was laid out for
+    bool adaptive = true;   // run_kernel launch plan from the previous launch's per-column cost
+    bool have_cost = false; // a previous hb_run left per-column costs on the device
+    int fast_flags = 0;     // HB_FAST_* (fast mode, never the default)
 };
 
 template <typename T>
@@ -112,25 +205,47 @@ static int dev_alloc(hb_ctx *ctx, T **p, size_t n)
 
 // (Re)allocate a named buffer only when it has to grow: repeated hb_set_* calls
 // (every benchmark step re-uploads its inputs) must not leak device memory.
+// Buffers the caller overwrites completely right away pass zero = false; result
+// buffers are cleared when they are (re)allocated or when their shape changes.
 template <typename T, typename SlotT>
-static int slot_alloc(hb_ctx *ctx, SlotT &s, T **p, size_t n)
+static int slot_alloc(hb_ctx *ctx, SlotT &s, T **p, size_t n, bool zero)
 {
     const size_t need = n * sizeof(T) + 16;
     if (s.bytes < need) {
         if (s.p) { cudaFree(s.p); s.p = nullptr; s.bytes = 0; }
         CK(cudaMalloc(&s.p, need));
         s.bytes = need;
+        zero = true;
     }
-    CK(cudaMemsetAsync(s.p, 0, need, ctx->stream));
+    if (zero) CK(cudaMemsetAsync(s.p, 0, need, ctx->stream));
     *p = static_cast<T *>(s.p);
     return 0;
+}
+
+// Tuning knobs read from the environment (A/B experiments only): every active one
+// is reported on stderr so that a run never changes code paths silently.
+static const char *tuning_env(const char *name)
+{
+    const char *v = getenv(name);
+    if (v && *v) {
+        static bool told[8] = {false};
+        static const char *names[8] = {"HB_CARVEOUT", "HB_VARIANT", "HB_NO_FIXED", "HB_NO_TRI13", "HB_CHUNK",
+                                       "HB_DBG", "HB_NO_ADAPTIVE", "HB_TRI_DEBUG"};
+        for (int k = 0; k < 8; ++k)
+            if (!strcmp(names[k], name) && !told[k]) {
+                told[k] = true;
+                fprintf(stderr, "[libhydrob200] tuning knob %s=%s is active\n", name, v);
+            }
+        return v;
+    }
+    return nullptr;
 }
 
 template <typename K>
 static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
 {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
-    if (const char *v = getenv("HB_CARVEOUT"))            // tuning experiments: shared-memory carve-out in percent
+    if (const char *v = tuning_env("HB_CARVEOUT"))            // tuning experiments: shared-memory carve-out in percent
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nt, ctx->smem_bytes));
@@ -174,7 +289,7 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
 extern "C" {
 
 const char *hb_last_error(void) { return g_err.c_str(); }
-int hb_version(void) { return 100; }
+int hb_version(void) { return 200; }
 int hb_max_nx(void) { return 1536; }
 
 hb_ctx *hb_create(int device, int nx, int n_cols)
@@ -194,15 +309,15 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.nx = nx; d.nxp = (nx + 1) & ~1; d.n_cols = n_cols;
     // 385..416 nodes (the reference's 401-node default): pad every vector to
     // 32 x 13 rows so that the tridiagonal solver runs its unrolled variant
-    if (nx > 32 * 12 && nx <= 32 * 13 && !getenv("HB_NO_TRI13")) d.nxp = 32 * 13;
+    if (nx > 32 * 12 && nx <= 32 * 13 && !tuning_env("HB_NO_TRI13")) d.nxp = 32 * 13;
     d.rtol = 1e-3; d.atol = 1e-3; d.sqrt_nx = sqrt((double)nx);
     d.newton_tol = fmax(10.0 * HB_EPS / d.rtol, fmin(0.03, sqrt(d.rtol)));
     ctx->variant = nx <= 448 ? 0 : (nx <= 512 ? 1 : (nx <= 1024 ? 2 : 3));
-    if (const char *v = getenv("HB_VARIANT")) {          // tuning experiments
+    if (const char *v = tuning_env("HB_VARIANT")) {          // tuning experiments
         const int want = atoi(v);
         if (nx <= 512 && want == 1) ctx->variant = 1;
     }
-    ctx->fixed = ctx->variant == 0 && d.nxp == HB_FIXED_NXP && !getenv("HB_NO_FIXED");
+    ctx->fixed = ctx->variant == 0 && d.nxp == HB_FIXED_NXP && !tuning_env("HB_NO_FIXED");
     ctx->smem_bytes = smem_doubles(d.nxp, ctx->variant == 0) * sizeof(double);
     {   // BDF coefficient tables exactly as scipy builds them (bdf.py:244-247)
         const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
@@ -221,7 +336,8 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     }
     ctx->stream = ctx->own_stream;
     int rc = 0;
-    double *x, *dx, *zx, *xz, *par, *stat, *psi, *nb; int *grp, *queue, *slot, *done; long long *cnt;
+    double *x, *dx, *zx, *xz, *par, *stat, *psi, *nb; int *grp, *queue, *slot, *done, *credit, *order, *nhot, *errf;
+    long long *cnt, *cost;
     rc |= dev_alloc(ctx, &x, nx); rc |= dev_alloc(ctx, &dx, nx); rc |= dev_alloc(ctx, &zx, nx);
     rc |= dev_alloc(ctx, &xz, nx); rc |= dev_alloc(ctx, &grp, nx);
     rc |= dev_alloc(ctx, &par, (size_t)n_cols * HB_NPARAM);
@@ -229,6 +345,8 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     rc |= dev_alloc(ctx, &psi, (size_t)n_cols * nx);
     rc |= dev_alloc(ctx, &nb, (size_t)n_cols * nx);
     rc |= dev_alloc(ctx, &queue, 4); rc |= dev_alloc(ctx, &slot, n_cols); rc |= dev_alloc(ctx, &done, n_cols);
+    rc |= dev_alloc(ctx, &credit, n_cols); rc |= dev_alloc(ctx, &order, n_cols); rc |= dev_alloc(ctx, &nhot, 4);
+    rc |= dev_alloc(ctx, &errf, 4); rc |= dev_alloc(ctx, &cost, n_cols);
     rc |= dev_alloc(ctx, &cnt, (size_t)n_cols * HB_NCOUNTER);
     rc |= dev_alloc(ctx, &ctx->hook_io, (size_t)8 * nx + 8);
     rc |= dev_alloc(ctx, &ctx->hook_stats, HB_NCOUNTER + 2);
@@ -236,11 +354,13 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.x = x; d.dx = dx; d.zx = zx; d.xz = xz; d.grp = grp; d.par = par; d.stat = stat;
     d.psi = psi; d.noise_base = nb; d.queue = queue; d.slot_next = slot; d.counters = cnt;
     d.done = done; d.chunk = 16;
+    d.credit = credit; d.order = order; d.n_hot = nhot; d.err_flags = errf; d.cost = cost;
+    if (tuning_env("HB_NO_ADAPTIVE")) ctx->adaptive = false;
     { long long *pc; if (dev_alloc(ctx, &pc, 16)) { hb_destroy(ctx); return nullptr; } d.phase_cycles = pc; }
-    if (const char *v = getenv("HB_CHUNK")) { const int w = atoi(v); if (w > 0) d.chunk = w; }
+    if (const char *v = tuning_env("HB_CHUNK")) { const int w = atoi(v); if (w > 0) d.chunk = w; }
     d.dbg = 0;
 #if HB_DUP_PROBE
-    if (const char *v = getenv("HB_DBG")) d.dbg = atoi(v);
+    if (const char *v = tuning_env("HB_DBG")) d.dbg = atoi(v);
 #endif
     d.noise_mode = HB_NOISE_TAPE; d.n_slots = 0; d.tape = nullptr;
     HB_FOR_VARIANT(ctx, {
@@ -264,7 +384,7 @@ int hb_destroy(hb_ctx *ctx)
     cudaDeviceSynchronize();
     for (void *p : ctx->allocs) cudaFree(p);
     for (auto *sl : {&ctx->s_precip, &ctx->s_atm, &ctx->s_wtd, &ctx->s_day, &ctx->s_series, &ctx->s_wscal,
-                     &ctx->s_fields, &ctx->s_tape, &ctx->s_nr0, &ctx->s_zw, &ctx->s_it})
+                     &ctx->s_fields, &ctx->s_tape, &ctx->s_nr0, &ctx->s_zw, &ctx->s_it, &ctx->s_mom})
         if (sl->p) cudaFree(sl->p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -278,13 +398,27 @@ int hb_set_stream(hb_ctx *ctx, void *s)
     return 0;
 }
 
+// Wait for the stream and turn error bits raised by kernels into a failure.
+static int finish(hb_ctx *ctx)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    int flags = 0;
+    CK(cudaMemcpyAsync(&flags, ctx->d.err_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flags & HB_ERR_TAPE_SHORT) {
+        CK(cudaMemsetAsync(ctx->d.err_flags, 0, sizeof(int), ctx->stream));
+        return fail("noise tape too short: a column refreshed its field more often than the tape has slots "
+                    "(hb_set_noise_tape n_slots; count the refresh rows with the column's precipitation multiplier)");
+    }
+    return 0;
+}
+
 int hb_sync(hb_ctx *ctx)
 {
     if (!ctx) return fail("null ctx");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    return 0;
+    return finish(ctx);
 }
 
 int hb_set_grid(hb_ctx *ctx, const double *x, const int32_t *groups, int n_groups)
@@ -367,9 +501,7 @@ int hb_get_state(hb_ctx *ctx, int col0, int ncol, double *psi)
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(psi, ctx->d.psi + (size_t)col0 * ctx->d.nx, (size_t)ncol * ctx->d.nx * sizeof(double),
                        cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    return 0;
+    return finish(ctx);
 }
 
 int hb_set_forcing(hb_ctx *ctx, int n_series, int T, const double *precip, const int32_t *wtd_idx,
@@ -386,14 +518,14 @@ int hb_set_forcing(hb_ctx *ctx, int n_series, int T, const double *precip, const
             if (series_of_col[k] < 0 || series_of_col[k] >= n_series) return fail("hb_set_forcing: bad series id");
     CK(cudaSetDevice(ctx->device));
     double *p, *a; int *w, *dl, *s = nullptr;
-    if (slot_alloc(ctx, ctx->s_precip, &p, n) || slot_alloc(ctx, ctx->s_atm, &a, n) ||
-        slot_alloc(ctx, ctx->s_wtd, &w, n) || slot_alloc(ctx, ctx->s_day, &dl, n)) return -1;
+    if (slot_alloc(ctx, ctx->s_precip, &p, n, false) || slot_alloc(ctx, ctx->s_atm, &a, n, !atm) ||
+        slot_alloc(ctx, ctx->s_wtd, &w, n, false) || slot_alloc(ctx, ctx->s_day, &dl, n, false)) return -1;
     CK(cudaMemcpyAsync(p, precip, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (atm) CK(cudaMemcpyAsync(a, atm, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(w, wtd_idx, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dl, daylight, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (series_of_col) {
-        if (slot_alloc(ctx, ctx->s_series, &s, (size_t)d.n_cols)) return -1;
+        if (slot_alloc(ctx, ctx->s_series, &s, (size_t)d.n_cols, false)) return -1;
         CK(cudaMemcpyAsync(s, series_of_col, d.n_cols * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -401,9 +533,14 @@ int hb_set_forcing(hb_ctx *ctx, int n_series, int T, const double *precip, const
     d.n_series = n_series; d.T = T;
     ctx->h_daylight.assign(daylight, daylight + n);
     if (series_of_col) ctx->h_series.assign(series_of_col, series_of_col + d.n_cols); else ctx->h_series.clear();
+    // per-row results: cleared only when the table length changes (a re-upload of the same
+    // forcing between launches keeps the rows already written)
     double *ws;
-    if (slot_alloc(ctx, ctx->s_wscal, &ws, (size_t)d.n_cols * T * HB_NWSCAL)) return -1;
-    d.wscal = ws; d.fields = nullptr; d.n_out = 0; d.out_stride = 0;
+    const bool new_shape = !ctx->forcing_set || ctx->wscal_T != T;
+    if (slot_alloc(ctx, ctx->s_wscal, &ws, (size_t)d.n_cols * T * HB_NWSCAL, new_shape)) return -1;
+    ctx->wscal_T = T;
+    d.wscal = ws;
+    if (new_shape) { d.fields = nullptr; d.n_out = 0; d.out_stride = 0; }
     ctx->forcing_set = true;
     return 0;
 }
@@ -416,7 +553,7 @@ int hb_set_noise_tape(hb_ctx *ctx, int col0, int ncol, int n_slots, const double
     CK(cudaSetDevice(ctx->device));
     if (d.n_slots != n_slots || !d.tape) {
         double *t;
-        if (slot_alloc(ctx, ctx->s_tape, &t, (size_t)d.n_cols * n_slots * d.nx)) return -1;
+        if (slot_alloc(ctx, ctx->s_tape, &t, (size_t)d.n_cols * n_slots * d.nx, false)) return -1;
         d.tape = t; d.n_slots = n_slots;
     }
     CK(cudaMemcpyAsync((void *)(d.tape + (size_t)col0 * n_slots * d.nx), tape,
@@ -449,11 +586,13 @@ int hb_set_output(hb_ctx *ctx, int out_stride)
     if (!ctx || !ctx->forcing_set) return fail("hb_set_output: call hb_set_forcing first");
     DevCtx &d = ctx->d;
     if (out_stride <= 0) { d.out_stride = 0; d.n_out = 0; d.fields = nullptr; return 0; }
+    const int n_out = (d.T - 1) / out_stride + 1 + (((d.T - 1) % out_stride) != 0);
+    const bool new_shape = !d.fields || d.out_stride != out_stride || d.n_out != n_out;
     d.out_stride = out_stride;
-    d.n_out = (d.T - 1) / out_stride + 1 + (((d.T - 1) % out_stride) != 0);
+    d.n_out = n_out;
     double *f;
     CK(cudaSetDevice(ctx->device));
-    if (slot_alloc(ctx, ctx->s_fields, &f, (size_t)d.n_cols * d.n_out * HB_NFIELD * d.nx)) return -1;
+    if (slot_alloc(ctx, ctx->s_fields, &f, (size_t)d.n_cols * d.n_out * HB_NFIELD * d.nx, new_shape)) return -1;
     d.fields = f;
     return 0;
 }
@@ -498,12 +637,12 @@ int hb_spinup(hb_ctx *ctx, int max_iter, const double *nrnd0, const double *zwtd
     CK(cudaSetDevice(ctx->device));
     double *nr = nullptr, *zw; int *it;
     if (nrnd0) {
-        if (slot_alloc(ctx, ctx->s_nr0, &nr, (size_t)d.n_cols * d.nx)) return -1;
+        if (slot_alloc(ctx, ctx->s_nr0, &nr, (size_t)d.n_cols * d.nx, false)) return -1;
         CK(cudaMemcpyAsync(nr, nrnd0, (size_t)d.n_cols * d.nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (slot_alloc(ctx, ctx->s_zw, &zw, (size_t)d.n_cols) || slot_alloc(ctx, ctx->s_it, &it, (size_t)d.n_cols)) return -1;
+    if (slot_alloc(ctx, ctx->s_zw, &zw, (size_t)d.n_cols, false) || slot_alloc(ctx, ctx->s_it, &it, (size_t)d.n_cols, true)) return -1;
     CK(cudaMemcpyAsync(zw, zwtd0_cm, d.n_cols * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(d.queue, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d.queue, 0, 2 * sizeof(int), ctx->stream));
     const int grid = persistent_grid(ctx);
     DISPATCH(ctx, spinup_kernel, grid, d, max_iter, nr, zw, it);
     CK(cudaGetLastError());
@@ -524,49 +663,77 @@ int hb_run(hb_ctx *ctx, int w0, int w1)
     if (d.noise_mode == HB_NOISE_TAPE && !d.tape) return fail("hb_run: noise not set");
     if (sinks_supported(ctx, w0, w1)) return -1;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemsetAsync(d.queue, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d.queue, 0, 2 * sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(d.done, 0, (size_t)d.n_cols * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d.credit, 0, (size_t)d.n_cols * sizeof(int), ctx->stream));
     const int grid = persistent_grid(ctx);
-    DISPATCH(ctx, run_kernel, grid, d, w0, w1);
+    DevCtx k = d;
+    if (ctx->adaptive && ctx->have_cost && d.n_cols > grid) {
+        // columns the previous launch found expensive start first and run unpaced
+        plan_kernel<<<1, 1024, 0, ctx->stream>>>(d, grid / 2);
+        ctx->launches++;
+    } else {
+        k.order = nullptr;
+        CK(cudaMemsetAsync(d.cost, 0, (size_t)d.n_cols * sizeof(long long), ctx->stream));
+    }
+    DISPATCH(ctx, run_kernel, grid, k, w0, w1);
     CK(cudaGetLastError());
+    ctx->have_cost = true;
     return 0;
 }
 
-int hb_get_wscal(hb_ctx *ctx, int col0, int ncol, double *wscal)
+int hb_get_wscal_rows(hb_ctx *ctx, int col0, int ncol, int row0, int nrow, double *wscal)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
     if (!ctx->forcing_set) return fail("hb_get_wscal: forcing not set");
     if (!wscal) return fail("hb_get_wscal: null argument");
-    const size_t per = (size_t)ctx->d.T * HB_NWSCAL;
+    if (row0 < 0 || nrow < 0 || row0 + nrow > ctx->d.T) return fail("hb_get_wscal: row range out of bounds");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(wscal, ctx->d.wscal + col0 * per, ncol * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    return 0;
+    if (ncol > 0 && nrow > 0) {
+        const size_t pitch = (size_t)ctx->d.T * HB_NWSCAL * sizeof(double), width = (size_t)nrow * HB_NWSCAL * sizeof(double);
+        CK(cudaMemcpy2DAsync(wscal, width, ctx->d.wscal + ((size_t)col0 * ctx->d.T + row0) * HB_NWSCAL, pitch, width,
+                             (size_t)ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return finish(ctx);
 }
 
-int hb_get_fields(hb_ctx *ctx, int col0, int ncol, double *fields)
+int hb_get_wscal(hb_ctx *ctx, int col0, int ncol, double *wscal)
+{
+    if (!ctx) return fail("null ctx");
+    return hb_get_wscal_rows(ctx, col0, ncol, 0, ctx->d.T, wscal);
+}
+
+int hb_get_fields_rows(hb_ctx *ctx, int col0, int ncol, int out0, int nout, double *fields)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
     if (!ctx->d.fields) return fail("hb_get_fields: no field output planned (hb_set_output)");
     if (!fields) return fail("hb_get_fields: null argument");
-    const size_t per = (size_t)ctx->d.n_out * HB_NFIELD * ctx->d.nx;
+    if (out0 < 0 || nout < 0 || out0 + nout > ctx->d.n_out) return fail("hb_get_fields: output-row range out of bounds");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(fields, ctx->d.fields + col0 * per, ncol * per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    return 0;
+    if (ncol > 0 && nout > 0) {
+        const size_t row_bytes = (size_t)HB_NFIELD * ctx->d.nx * sizeof(double);
+        const size_t pitch = (size_t)ctx->d.n_out * row_bytes, width = (size_t)nout * row_bytes;
+        CK(cudaMemcpy2DAsync(fields, width,
+                             ctx->d.fields + ((size_t)col0 * ctx->d.n_out + out0) * HB_NFIELD * ctx->d.nx, pitch, width,
+                             (size_t)ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return finish(ctx);
+}
+
+int hb_get_fields(hb_ctx *ctx, int col0, int ncol, double *fields)
+{
+    if (!ctx) return fail("null ctx");
+    return hb_get_fields_rows(ctx, col0, ncol, 0, ctx->d.n_out, fields);
 }
 
 int hb_get_counters(hb_ctx *ctx, int col0, int ncol, int64_t *counters)
 {
     if (range_ok(ctx, col0, ncol)) return -1;
+    if (!counters) return fail("hb_get_counters: null argument");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(counters, ctx->d.counters + (size_t)col0 * HB_NCOUNTER,
                        (size_t)ncol * HB_NCOUNTER * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    return 0;
+    return finish(ctx);
 }
 
 int hb_reset_counters(hb_ctx *ctx)
@@ -577,12 +744,45 @@ int hb_reset_counters(hb_ctx *ctx)
     return 0;
 }
 
-int hb_wtd_moments_dev(hb_ctx *ctx, double *sum_dev, double *sumsq_dev)
+int hb_set_schedule(hb_ctx *ctx, int adaptive)
 {
-    if (!ctx || !ctx->forcing_set) return fail("hb_wtd_moments_dev: forcing not set");
+    if (!ctx) return fail("null ctx");
+    ctx->adaptive = adaptive != 0;
+    ctx->have_cost = false;
+    return 0;
+}
+
+int hb_moments_dev(hb_ctx *ctx, double *count_dev, double *wtd_sum_dev, double *wtd_sumsq_dev,
+                   double *theta_sum_dev, double *theta_sumsq_dev)
+{
+    if (!ctx || !ctx->forcing_set) return fail("hb_moments_dev: forcing not set");
+    if (!wtd_sum_dev || !wtd_sumsq_dev) return fail("hb_moments_dev: null argument");
+    if ((theta_sum_dev == nullptr) != (theta_sumsq_dev == nullptr)) return fail("hb_moments_dev: give both theta buffers or none");
+    if (theta_sum_dev && !ctx->d.fields) return fail("hb_moments_dev: no field output planned (hb_set_output)");
+    const DevCtx &d = ctx->d;
     CK(cudaSetDevice(ctx->device));
-    moments_kernel<<<(ctx->d.T + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, sum_dev, sumsq_dev);
-    ctx->launches++;
+    const int M_theta = theta_sum_dev ? d.n_out * d.nx : 0, M_max = d.T > M_theta ? d.T : M_theta;
+    // enough column slices to fill the GPU, at least 64 columns each
+    int n_slices = (4 * ctx->sms * 256 + M_max - 1) / M_max;
+    const int max_slices = (d.n_cols + 63) / 64;
+    if (n_slices > max_slices) n_slices = max_slices;
+    if (n_slices < 1) n_slices = 1;
+    const int per = (d.n_cols + n_slices - 1) / n_slices;
+    n_slices = (d.n_cols + per - 1) / per;
+    double *part;
+    if (slot_alloc(ctx, ctx->s_mom, &part, (size_t)n_slices * 3 * M_max, false)) return -1;
+    {
+        const dim3 grid((d.T + 255) / 256, n_slices);
+        moments_partial_kernel<false><<<grid, 256, 0, ctx->stream>>>(d, d.T, per, part);
+        moments_final_kernel<<<(d.T + 255) / 256, 256, 0, ctx->stream>>>(part, d.T, n_slices, count_dev, wtd_sum_dev, wtd_sumsq_dev);
+        ctx->launches += 2;
+    }
+    if (theta_sum_dev) {
+        const dim3 grid((M_theta + 255) / 256, n_slices);
+        moments_partial_kernel<true><<<grid, 256, 0, ctx->stream>>>(d, M_theta, per, part);
+        moments_final_kernel<<<(M_theta + 255) / 256, 256, 0, ctx->stream>>>(part, M_theta, n_slices, nullptr, theta_sum_dev, theta_sumsq_dev);
+        ctx->launches += 2;
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -593,8 +793,9 @@ int hb_get_phase_cycles(hb_ctx *ctx, int64_t *out16)
 {
     if (!ctx || !out16) return fail("hb_get_phase_cycles: null argument");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpy(out16, ctx->d.phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(ctx->d.phase_cycles, 0, 16 * sizeof(long long)));
+    CK(cudaMemcpyAsync(out16, ctx->d.phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d.phase_cycles, 0, 16 * sizeof(long long), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -704,12 +905,41 @@ int hb_tri_solve(hb_ctx *ctx, const double *dl, const double *d, const double *d
         hook_in(ctx, 3, d) || hook_in(ctx, 4, du) || hook_in(ctx, 5, b)) return -1;
     HookArgs h{}; h.mode = HK_TRI; h.col = 0; h.c = c;
     if (run_hook(ctx, h)) return -1;
-    if (getenv("HB_TRI_DEBUG")) {            // cycles: factor, then four repeated solves
+    if (tuning_env("HB_TRI_DEBUG")) {            // cycles: factor, then four repeated solves
         double t[5];
         CK(cudaMemcpy(t, ctx->hook_io + (size_t)7 * ctx->d.nx, sizeof(t), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[hb_tri_solve] cycles: factor %.0f, solve %.0f %.0f %.0f %.0f\n", t[0], t[1], t[2], t[3], t[4]);
     }
     return hook_out(ctx, 6, x, ctx->d.nx);
+}
+
+int hb_find_wtd(hb_ctx *ctx, int col, const double *psi, int32_t *wtd_node)
+{
+    if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
+    if (!psi || !wtd_node) return fail("hb_find_wtd: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (hook_in(ctx, 0, psi) || hook_in(ctx, 1, psi)) return -1;
+    HookArgs h{}; h.mode = HK_WTD; h.col = col;
+    if (run_hook(ctx, h)) return -1;
+    long long w = 0;
+    CK(cudaMemcpy(&w, ctx->hook_stats, sizeof(w), cudaMemcpyDeviceToHost));
+    *wtd_node = (int32_t)w;
+    return 0;
+}
+
+int hb_philox_normals(hb_ctx *ctx, uint64_t seed, int64_t global_column, int window, int n, double *out)
+{
+    if (!ctx || !out || n < 1) return fail("hb_philox_normals: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * sizeof(double)));
+    philox_probe_kernel<<<ctx->sms * 4, 256, 0, ctx->stream>>>(seed, global_column, window, n, d);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(std::string("hb_philox_normals: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 int hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0, double *nrnd,

@@ -38,6 +38,7 @@
 #include "../../include/hb_layout.h"
 
 #define HB_EPS 2.220446049250313e-16
+#define HB_ERR_TAPE_SHORT 1   // a column refreshed its noise field more often than the tape has slots
 #define HB_FULL 0xffffffffu
 
 // Everything a kernel needs, passed by value as a __grid_constant__ parameter
@@ -58,7 +59,12 @@ struct DevCtx {
     int *queue;
     long long *phase_cycles; // [16] summed phase timings (HB_PHASE_TIMING builds), else unused
     double *dbuf;            // [resident CTAs][G_ROWS][nxp] per-CTA global scratch (difference table, ...)
-    int *done;               // [n_cols] finished window-chunks per column (time-slicing)
+    int *done;               // [n_cols] finished row-chunks per column in this launch
+    int *credit;             // [n_cols] chunks granted but not yet integrated (run_kernel scheduler)
+    int *order;              // [n_cols] launch plan: hot columns first (plan_kernel), or null
+    int *n_hot;              // [1] number of hot columns in `order`
+    long long *cost;         // [n_cols] RHS evaluations per column in the current launch (next plan)
+    int *err_flags;          // [1] HB_ERR_* bits raised by kernels, checked by hb_sync / hb_get_*
     int chunk;               // windows per work item of run_kernel
     int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice
     double sqrt_nx;          // sqrt((double)nx), the denominator of the RMS norm

@@ -58,95 +58,126 @@ __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row,
     }
 }
 
-// Work item = (column, chunk of c.chunk consecutive rows).  Tickets are handed
-// out in chunk-major order, so a persistent CTA that finishes early keeps
-// pulling work and the tail of the launch is at most one chunk long (columns
-// differ in cost: step counts, retries).  Chunk j of a column may only start
-// when chunk j-1 is finished; its ticket is lower and therefore already held
-// by a running CTA, so the (rare) wait below cannot deadlock.
+// Work item = (column, chunk of c.chunk consecutive rows).  Scheduling is a credit
+// ("mailbox") scheme without spin-waits:
+//   * tickets come from one atomic counter.  The first c.n_hot tickets name the
+//     columns the previous launch found expensive (plan_kernel) and carry ALL
+//     their chunks, so that such a column starts at once and is never paced; the
+//     other tickets enumerate the remaining columns in chunk-major order, one
+//     chunk each -- a persistent CTA that finishes early keeps pulling work and
+//     the tail of the launch is one chunk long;
+//   * a ticket is a credit deposited on its column (atomicAdd).  Whoever finds
+//     the column idle (old credit 0) becomes its owner and integrates chunks
+//     until the credit is used up; a ticket for a busy column only leaves its
+//     credit behind -- the owner will run that chunk right after the current one
+//     (a column that falls behind therefore runs back to back, and nobody waits).
+// The chunks of a column are integrated in row order by one owner at a time; state,
+// base noise field and tape position are handed over through global memory
+// (release: __threadfence + atomic on the credit; acquire: the atomic + L2 loads).
 template <int NT, int CPT, int MB, bool FULL>
 __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
 {
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
-    __shared__ int s_ticket;
+    __shared__ int s_msg[2];
     const int nx = c.nx, tid = threadIdx.x;
     double *nr = HB_VEC(c, V_NR), *y = HB_VEC(c, V_Y);
     const int n_chunks = (w1 - w0 + c.chunk - 1) / c.chunk;
+    const int n_hot = c.order ? __ldcg(c.n_hot) : 0, n_reg = c.n_cols - n_hot;
+    const long long n_tickets = (long long)n_hot + (long long)n_reg * n_chunks;
     int parity = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(c.queue, 1);
-        __syncthreads();
-        const int ticket = s_ticket;
-        if (ticket >= c.n_cols * n_chunks) break;
-        const int chunk = ticket / c.n_cols, col = ticket % c.n_cols;
-        const int r0 = w0 + chunk * c.chunk, r1 = min(r0 + c.chunk, w1);
-        if (tid == 0 && chunk > 0) {
-            volatile int *dn = c.done + col;
-            while (*dn < chunk) __nanosleep(200);
-            __threadfence();
+        if (tid == 0) {
+            int col = -1;
+            const long long ticket = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(c.queue), 1ull);
+            if (ticket >= n_tickets) col = -2;
+            else {
+                int add = 1, pos;
+                if (ticket < n_hot) { pos = (int)ticket; add = n_chunks; }
+                else pos = n_hot + (int)((ticket - n_hot) % n_reg);
+                const int cand = c.order ? __ldcg(c.order + pos) : pos;
+                if (atomicAdd(c.credit + cand, add) == 0) { __threadfence(); col = cand; }
+            }
+            s_msg[0] = col;
         }
         __syncthreads();
+        const int col = s_msg[0];
+        if (col == -2) break;
+        if (col < 0) continue;                 // column busy: its owner takes the chunk
         bind_column<NT, FULL>(c, col);
         double *psi_g = c.psi + (size_t)col * nx;
         double *nb = c.noise_base + (size_t)col * nx;
-        for (int i = tid; i < nx; i += NT) { nr[i] = nb[i]; y[i] = __ldcg(psi_g + i); }
-        bool nr_is_base = true;
         const int ser = c.series ? c.series[col] : 0;
-        long long windows = 0;
-        __syncthreads();
-        for (int row = r0; row < r1; ++row) {
-            int status = 0;
-            bool solved = false;
-            if (row > 0) {
-                const int wtd = c.wtd_idx[(size_t)ser * c.T + row];
-                if (wtd < 0) status = 2;
-                else {
-                    const double p = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
-                    const bool refresh = (p > 0.5) || (row % 48 == 0);   // simulation.py:599
-                    __syncthreads();
-                    if (refresh) {
-                        if (c.noise_mode == HB_NOISE_TAPE) {
-                            const int slot = __ldcg(c.slot_next + col);          // uniform read
-                            const double *src = c.tape + ((size_t)col * c.n_slots + min(slot, c.n_slots - 1)) * nx;
-                            for (int i = tid; i < nx; i += NT) nr[i] = src[i];
-                            __syncthreads();
-                            if (tid == 0) c.slot_next[col] = slot + 1;
-                        } else {
-                            for (int i = tid; i < nx; i += NT)
-                                nr[i] = philox_normal(c.seed, c.col_offset + col, row, i);
+        bool more = true;
+        while (more) {
+            const int chunk = __ldcg(c.done + col);
+            const int r0 = w0 + chunk * c.chunk, r1 = min(r0 + c.chunk, w1);
+            __syncthreads();
+            if (tid < 8) reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT))[tid] = 0;
+            // L2 loads: another SM may have written the state and (after a failed solve)
+            // the damped base field
+            for (int i = tid; i < nx; i += NT) { nr[i] = __ldcg(nb + i); y[i] = __ldcg(psi_g + i); }
+            bool nr_is_base = true;
+            long long windows = 0;
+            __syncthreads();
+            for (int row = r0; row < r1; ++row) {
+                int status = 0;
+                bool solved = false;
+                if (row > 0) {
+                    const int wtd = c.wtd_idx[(size_t)ser * c.T + row];
+                    if (wtd < 0) status = 2;
+                    else {
+                        const double p = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
+                        const bool refresh = (p > 0.5) || (row % 48 == 0);   // simulation.py:599
+                        __syncthreads();
+                        if (refresh) {
+                            if (c.noise_mode == HB_NOISE_TAPE) {
+                                const int slot = __ldcg(c.slot_next + col);          // uniform read
+                                if (slot >= c.n_slots && tid == 0) atomicOr(c.err_flags, HB_ERR_TAPE_SHORT);
+                                const double *src = c.tape + ((size_t)col * c.n_slots + min(slot, c.n_slots - 1)) * nx;
+                                for (int i = tid; i < nx; i += NT) nr[i] = src[i];
+                                __syncthreads();
+                                if (tid == 0) __stcg(c.slot_next + col, slot + 1);
+                            } else {
+                                for (int i = tid; i < nx; i += NT)
+                                    nr[i] = philox_normal(c.seed, c.col_offset + col, row, i);
+                            }
+                            nr_is_base = false;
+                        } else if (!nr_is_base) {
+                            for (int i = tid; i < nx; i += NT) nr[i] = __ldcg(nb + i);
+                            nr_is_base = true;
                         }
-                        nr_is_base = false;
-                    } else if (!nr_is_base) {
-                        for (int i = tid; i < nx; i += NT) nr[i] = __ldcg(nb + i);
-                        nr_is_base = true;
+                        __syncthreads();
+                        Args a;
+                        a.precip = p; a.wtd = wtd;
+                        a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
+                        a.atm = c.atm ? c.atm[(size_t)ser * c.T + row] : 0.0;
+                        bool damped = false;
+                        status = solve_window<NT, CPT, FULL>(c, col, a, (double)(row - 1), (double)row, psi_g, damped);
+                        if (damped && nr_is_base)
+                            for (int i = tid; i < nx; i += NT) __stcg(nb + i, nr[i]);
+                        for (int i = tid; i < nx; i += NT) __stcg(psi_g + i, y[i]);
+                        windows++; solved = true;
                     }
-                    __syncthreads();
-                    Args a;
-                    a.precip = p; a.wtd = wtd;
-                    a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
-                    a.atm = c.atm ? c.atm[(size_t)ser * c.T + row] : 0.0;
-                    bool damped = false;
-                    status = solve_window<NT, CPT, FULL>(c, col, a, (double)(row - 1), (double)row, psi_g, damped);
-                    if (damped && nr_is_base)
-                        for (int i = tid; i < nx; i += NT) nb[i] = nr[i];
-                    for (int i = tid; i < nx; i += NT) psi_g[i] = y[i];
-                    windows++; solved = true;
                 }
+                write_row<NT, NV>(c, parity, col, row, status, solved);
             }
-            write_row<NT, NV>(c, parity, col, row, status, solved);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            add_counters(c.counters + (size_t)col * HB_NCOUNTER,
-                         reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT)), windows);
+            __syncthreads();
+            if (tid == 0) {
+                const long long *k = reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT));
+                add_counters(c.counters + (size_t)col * HB_NCOUNTER, k, windows);
+                if (c.cost) c.cost[col] += k[K_NRHS];          // owner-only: plain update
 #if HB_PHASE_TIMING
-            for (int k = 0; k < 15; ++k)
-                atomicAdd(reinterpret_cast<unsigned long long *>(c.phase_cycles) + k,
-                          (unsigned long long)reinterpret_cast<long long *>(HB_XA(c, NV, X_TIME))[k]);
+                for (int q = 0; q < 15; ++q)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(c.phase_cycles) + q,
+                              (unsigned long long)reinterpret_cast<long long *>(HB_XA(c, NV, X_TIME))[q]);
 #endif
-            __threadfence();                   // state, noise, counters before the hand-over
-            atomicExch(c.done + col, chunk + 1);
+                __stcg(c.done + col, chunk + 1);
+                __threadfence();                   // state, noise, counters, done before the hand-over
+                s_msg[1] = atomicSub(c.credit + col, 1) > 1;     // credit left: next chunk, same owner
+            }
+            __syncthreads();
+            more = s_msg[1] != 0;
         }
     }
 }
@@ -259,6 +290,10 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
         if (tid == 0) io[7 * nx] = (double)(t_f1 - t_f0);
         __syncthreads();
         for (int i = tid; i < nx; i += NT) io[6 * nx + i] = tri_x<NV, FULL>(c, i);
+    } else if (h.mode == HK_WTD) {
+        // find_wtd(y >= psi_sat) on the nodes (utilities.py:56-99) for the state in io[0..nx)
+        const int w = find_wtd_nodes<NT, NV>(c, parity, y);
+        if (tid == 0) h.stats[0] = w;
     } else if (h.mode == HK_WINDOW) {
         bool damped = false;
         const int st = solve_window<NT, CPT, FULL>(c, h.col, a, h.t0, h.t1, io, damped);

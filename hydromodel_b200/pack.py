@@ -219,7 +219,9 @@ def pack_forcing(objs, params, data):
     simulation.py:233-352)."""
     z = objs["z_grid"]
     stamps = pd.to_datetime(data.loc[:, "Datenum"] - 719529, unit="D")
-    times = [t.round(freq="s") for t in stamps]
+    stamps = pd.DatetimeIndex(stamps)
+    rounded = stamps.round(freq="s")
+    times = list(rounded)
     z_wtd = np.array(np.abs(np.round(100.0 * data.loc[:, "WTD_m"])))
     if np.any(np.isnan(z_wtd)):
         raise RuntimeError(" Simulation: Water table depth observations contain NaN values.")
@@ -231,7 +233,7 @@ def pack_forcing(objs, params, data):
         raise ValueError(" Simulation: Precipitation observations contain NaN values.")
     env = params["Environmental"]
     dim_t = len(times)
-    months = np.array([t.month for t in stamps])
+    months = np.asarray(stamps.month)
     dry = np.isin(months, (4, 5, 6, 7, 8, 9))
     total = 13.4253 * 10 * env["Atmospheric_Demand"]
     et_pct = np.minimum(np.maximum(env["Wet_Season_pct"], 0.0), 1.0)
@@ -240,7 +242,7 @@ def pack_forcing(objs, params, data):
         atm = np.where(dry, 2.0 * (1.0 - et_pct) * total / np.float64(n_dry),
                        2.0 * et_pct * total / np.float64(dim_t - n_dry))
     atm[np.isnan(atm)] = 0.0
-    hours = np.array([t.hour for t in times])
+    hours = np.asarray(rounded.hour)
     # node index of each snapped observation (always on the grid after
     # snapping; kept general: -1 marks "skip window", simulation.py:579-588)
     idx = np.searchsorted(z, snapped)
@@ -273,3 +275,209 @@ def saturated_initial_state(objs):
                            objs["theta"].res, objs["dz"])
     psi, _ = hm.pressure_head(objs["porosity"].profile, objs["z_grid"])
     return psi
+
+
+# ---------------------------------------------------------------------------
+# Ensembles: the same packing for many columns at once (array operations over
+# the column axis; per-column Python work is O(1) scalars only).
+# ---------------------------------------------------------------------------
+ENSEMBLE_KEYS = {          # per-column key -> (parameter group, name in the JSON)
+    "n": ("Soil_Properties", "n"), "a0": ("Soil_Properties", "a0"),
+    "psi_sat": ("Soil_Properties", "psi_sat"), "epsilon": ("Soil_Properties", "epsilon"),
+    "Theta_Max": ("Water_Content", "Theta_Max"), "Theta_Min": ("Water_Content", "Theta_Min"),
+    "Theta_Residual": ("Water_Content", "Theta_Residual"),
+    "model": ("Hydrological_Model", "Name"), "profile": ("Hydrological_Model", "Porosity_Profile"),
+    "precip_mult": (None, None),
+}
+_PROFILE_KINDS = ("CONSTANT", "LINEAR", "EXPONENTIAL", "STRATIFIED")
+
+
+def member_params(base_params, columns, k):
+    """The ``input_parameters`` dict of column ``k`` of a struct-of-arrays
+    ensemble and its precipitation multiplier."""
+    import copy
+    p = copy.deepcopy(base_params)
+    for key, arr in columns.items():
+        group, name = ENSEMBLE_KEYS[key]
+        if group is not None:
+            v = arr[k]
+            p[group][name] = v if isinstance(v, str) else float(v)
+    mult = float(columns["precip_mult"][k]) if "precip_mult" in columns else 1.0
+    return p, mult
+
+
+def _retention_scalar(alpha, n, m, suction):
+    """(1 + (alpha*psi)**n)**m with the scalar arithmetic of the reference
+    (porosity.py:172-181: Python/NumPy scalar pow); None when it goes complex."""
+    try:
+        d = (1.0 + (alpha * suction) ** n) ** m
+    except (OverflowError, ZeroDivisionError):
+        return None
+    if isinstance(d, complex) or not np.isfinite(d):
+        return None
+    return float(d)
+
+
+def pack_ensemble(base_params, data, columns, quiet=True, block=8192, _base=None):
+    """Pack ``C`` columns that differ from ``base_params`` only in the keys of
+    ``ENSEMBLE_KEYS`` (``columns``: key -> array of length C).  Returns the same
+    arrays as ``C`` calls of ``pack_column`` would -- bit for bit, see
+    tests/test_host_objects.py -- as ``par[C, NPARAM]``, ``stat[C, NSTATIC, nx]``
+    plus the shared grid / forcing / objects of the base column.
+
+    Columns whose parameter groups are invalid (the reference then falls back
+    to defaults, simulation.py:100-231) or whose field-capacity formula leaves
+    the reals (quirk Q7) are packed one by one through ``pack_column``.
+    """
+    unknown = set(columns) - set(ENSEMBLE_KEYS)
+    if unknown:
+        raise KeyError(f" pack_ensemble: unsupported per-column keys {sorted(unknown)}")
+    sizes = {np.asarray(v).shape[0] for v in columns.values()}
+    if len(sizes) != 1:
+        raise ValueError(" pack_ensemble: per-column arrays must share one length.")
+    C = sizes.pop()
+    base = _base if _base is not None else pack_column(base_params, data, quiet=quiet)
+    objs, forcing = base["objs"], base["forcing"]
+    if C > block:                      # bounded temporaries: pack block by block
+        nx_ = objs["z_grid"].size
+        par, stat, n_slow = np.empty((C, NPARAM)), np.empty((C, NSTATIC, nx_)), 0
+        for lo in range(0, C, block):
+            part = pack_ensemble(base_params, data, {k: np.asarray(v)[lo:lo + block] for k, v in columns.items()},
+                                 quiet=quiet, block=block, _base=base)
+            par[lo:lo + block], stat[lo:lo + block] = part["par"], part["stat"]
+            n_slow += part["n_slow"]
+        return {"objs": objs, "forcing": forcing, "par": par, "stat": stat,
+                "x": objs["z_grid"].astype(np.float64), "n_slow": n_slow}
+    z, nx = objs["z_grid"], objs["z_grid"].size
+    k_hc, theta0, soil0 = objs["K"], objs["theta"], objs["soil"]
+    sp, wc = base_params["Soil_Properties"], base_params["Water_Content"]
+
+    def col(key, default):
+        if key in columns:
+            return np.asarray(columns[key], dtype=np.float64)
+        return np.full(C, float(default))
+
+    n, a0 = col("n", sp["n"]), col("a0", sp["a0"])
+    psi_sat, eps = col("psi_sat", sp["psi_sat"]), col("epsilon", sp["epsilon"])
+    th_max = np.maximum(np.minimum(1.0, col("Theta_Max", wc["Theta_Max"])), 0.0)
+    th_min = np.maximum(np.minimum(1.0, col("Theta_Min", wc["Theta_Min"])), 0.0)
+    th_res = np.maximum(np.minimum(1.0, col("Theta_Residual", wc["Theta_Residual"])), 0.0)
+    mult = col("precip_mult", 1.0)
+    flc, wlt = wc["Field_Capacity_cm"], wc["Wilting_Point_cm"]
+    hm = base_params["Hydrological_Model"]
+    kinds = np.array([str.upper(str(v)) for v in columns["profile"]]) if "profile" in columns \
+        else np.full(C, str.upper(hm["Porosity_Profile"]))
+    model_id = np.array([0.0 if str.upper(str(v)) == "VRETTAS_FUNG" else 1.0 for v in columns["model"]]) \
+        if "model" in columns else np.full(C, float(objs["model_id"]))
+
+    # columns the array path cannot reproduce: invalid groups, NOISY, complex field capacity
+    slow = ~((n > 1.0) & (a0 > 0.0) & (0.0 <= th_res) & (th_res < th_min) & (th_min < th_max) &
+             (th_max <= 1.0) & np.isin(kinds, _PROFILE_KINDS))
+    m = 1.0 - (1.0 / n)
+    d_flc, d_wlt = np.ones(C), np.ones(C)
+    for k in range(C):
+        if slow[k]:
+            continue
+        a, b = _retention_scalar(float(a0[k]), float(n[k]), float(m[k]), flc), \
+            _retention_scalar(float(a0[k]), float(n[k]), float(m[k]), wlt)
+        if a is None or b is None:
+            slow[k] = True
+        else:
+            d_flc[k], d_wlt[k] = a, b
+
+    # ---- porosity profiles at the nodes, by profile type (porosity.py:22-185) ----
+    l0, l_sapr, l_wbed, l_fbed = objs["layers"]
+    in_sapr = (z >= l_sapr) & (z <= l_wbed)
+    in_wbed = (z >= l_wbed) & (z <= l_fbed)
+    th_mid = 0.5 * (th_max + th_min)
+    q_sat = np.empty((C, nx))
+    for kind in _PROFILE_KINDS:
+        sel = np.flatnonzero((kinds == kind) & ~slow)
+        if not sel.size:
+            continue
+        mx, mn, md = th_max[sel, None], th_min[sel, None], th_mid[sel, None]
+        if kind == "CONSTANT":
+            q = mx * np.ones(nx)
+        elif kind == "LINEAR":
+            q = np.linspace(th_max[sel], th_min[sel], nx, axis=1)
+        elif kind == "EXPONENTIAL":
+            q = mx * np.exp(-z[None, :] * (np.log(mx / mn) / z[-1]))
+        else:
+            q = mx * np.ones(nx)
+            if np.any(in_sapr):
+                q[:, in_sapr] = np.linspace(th_max[sel], th_mid[sel], int(in_sapr.sum()), axis=1)
+            if np.any(in_wbed):
+                rate = np.log(md / mn) / z[-1]
+                q[:, in_wbed] = md * np.exp(-np.linspace(0, l_fbed, int(in_wbed.sum()))[None, :] * rate)
+        q_sat[sel] = np.minimum(np.maximum(q, mn), mx)
+    res = th_res[:, None]
+    with np.errstate(all="ignore"):
+        f_cap = np.maximum(res + (q_sat - res) / d_flc[:, None], res)
+        wilt = np.minimum(res + (q_sat - res) / d_wlt[:, None], f_cap)
+
+    # ---- static cell arrays: shared rows from the base column, porosity rows per column ----
+    stat = np.empty((C, NSTATIC, nx))
+    stat[:] = base["stat"][None]
+    x_mid = z[:-1] + 0.5 * np.diff(z)
+    prof_mid = lerp_table(z, np.stack((q_sat, f_cap, wilt), axis=1), x_mid)     # [C, 3, nx-1]
+    stat[:, S_PHI_MID, :-1] = prof_mid[:, 0]
+    stat[:, S_FCAP_MID, :-1] = prof_mid[:, 1]
+    stat[:, S_WILT_MID, :-1] = prof_mid[:, 2]
+    stat[:, S_PHI_MID, -1] = q_sat[:, -1]
+    stat[:, S_PHI_NODE] = q_sat
+
+    # ---- scalar blocks ----
+    par = np.empty((C, NPARAM))
+    par[:] = base["par"][None]
+    par[:, P_N], par[:, P_M], par[:, P_ALPHA] = n, m, a0
+    par[:, P_PSI_SAT] = np.minimum(psi_sat, 0.0)
+    par[:, P_EPS] = np.maximum(np.maximum(eps, 1.0e-8), 1.0e-8)
+    par[:, P_THETA_RES] = th_res
+    par[:, P_MODEL], par[:, P_PRECIP_MULT] = model_id, mult
+    par[:, P_PHI_TOP] = q_sat[:, 0]
+    ds = q_sat - res
+    if z[0] == 0.0:
+        par[:, P_DSMIN_ALL] = ds.min(axis=1)
+        par[:, P_DSMIN_EXCL0] = ds[:, 1:].min(axis=1) if nx > 1 else ds[:, 0]
+    else:
+        par[:, P_DSMIN_ALL] = par[:, P_DSMIN_EXCL0] = ds[:, 0]
+    theta_50 = np.maximum(0.5 ** (1.0 / k_hc.lambda_exponent), 0.05) \
+        if k_hc.lambda_exponent > 0 else 0.05
+    par[:, P_IPSI50] = a0 / np.sqrt(theta_50 ** (-2.0) - 1.0)
+
+    for k in np.flatnonzero(slow):
+        p, mk = member_params(base_params, columns, k)
+        one = pack_column(p, data, precip_mult=mk, quiet=quiet)
+        par[k], stat[k] = one["par"], one["stat"]
+    return {"objs": objs, "forcing": forcing, "par": par, "stat": stat,
+            "x": z.astype(np.float64), "n_slow": int(slow.sum())}
+
+
+def split_params_list(params_list):
+    """Group a list of ``input_parameters`` dicts by everything that is NOT a
+    per-column key of ``pack_ensemble``: returns ``[(base, columns, indices)]``
+    so that each group can be packed with array operations."""
+    groups = {}
+    for idx, p in enumerate(params_list):
+        shared = {g: ({k: v for k, v in blk.items()
+                       if (g, k) not in _ENSEMBLE_PAIRS} if isinstance(blk, dict) else blk)
+                  for g, blk in p.items()}
+        sig = json.dumps(shared, sort_keys=True, default=str)
+        groups.setdefault(sig, []).append(idx)
+    out = []
+    for idxs in groups.values():
+        base = params_list[idxs[0]]
+        cols = {}
+        for key, (g, name) in ENSEMBLE_KEYS.items():
+            if g is None:
+                continue
+            vals = [params_list[i][g][name] for i in idxs]
+            if isinstance(vals[0], str):
+                cols[key] = np.array(vals, dtype=object)
+            else:
+                cols[key] = np.array(vals, dtype=np.float64)
+        out.append((base, cols, np.array(idxs)))
+    return out
+
+
+_ENSEMBLE_PAIRS = {v for v in ENSEMBLE_KEYS.values() if v[0] is not None}

@@ -90,34 +90,86 @@ def _log_uniform(rng, lo, hi):
     return float(np.exp(rng.uniform(np.log(lo), np.log(hi))))
 
 
-def ensemble_member(base_params, column, n_columns, mixed=False,
+def _member_rng(column, seed):
+    """Generator of ensemble column ``column``: child ``column`` of
+    ``SeedSequence(seed).spawn(...)``, built directly from its spawn key (the
+    stream does not depend on how many columns the ensemble has)."""
+    return np.random.default_rng(np.random.SeedSequence(seed, spawn_key=(int(column),)))
+
+
+_MODELS = ("vrettas_fung", "vanGenuchten")
+_PROFILES = ("Constant", "Linear", "Exponential", "Stratified")
+
+
+def _member_draws(rng, mixed, perturb_theta):
+    """Draw order per column stream: n, a0, psi_sat, [Theta_Max, precip
+    multiplier], [model, profile]."""
+    n = float(rng.uniform(1.6, 2.6))
+    a0 = _log_uniform(rng, 0.005, 0.015)
+    psi_sat = -_log_uniform(rng, 1.0e-3, 1.0)
+    theta_max, mult, model, profile = None, 1.0, None, None
+    if perturb_theta:
+        theta_max = float(rng.uniform(0.25, 0.35))
+        mult = float(np.exp(0.2 * rng.standard_normal()))
+    if mixed:
+        model = int(rng.integers(2))
+        profile = int(rng.integers(4))
+    return n, a0, psi_sat, theta_max, mult, model, profile
+
+
+def ensemble_member(base_params, column, n_columns=None, mixed=False,
                     perturb_theta=False, seed=ENSEMBLE_SEED):
     """Parameters of ensemble column ``column``.
 
-    Draw order per column stream: n, a0, psi_sat, [Theta_Max, precip
-    multiplier], [model, profile].  Returns ``(params, precip_multiplier)``.
+    Returns ``(params, precip_multiplier)``.  ``n_columns`` is accepted for
+    compatibility and ignored: a member depends on its global id only.
     The wilting point is set to +1500 cm: the reference's field-capacity
     formula goes complex for non-even ``n`` with the default -1500
     (porosity.py:172-181).
     """
-    child = np.random.SeedSequence(seed).spawn(n_columns)[column]
-    rng = np.random.default_rng(child)
+    n, a0, psi_sat, theta_max, mult, model, profile = \
+        _member_draws(_member_rng(column, seed), mixed, perturb_theta)
     p = copy.deepcopy(base_params)
-    p["Soil_Properties"]["n"] = float(rng.uniform(1.6, 2.6))
-    p["Soil_Properties"]["a0"] = _log_uniform(rng, 0.005, 0.015)
-    p["Soil_Properties"]["psi_sat"] = -_log_uniform(rng, 1.0e-3, 1.0)
+    p["Soil_Properties"]["n"] = n
+    p["Soil_Properties"]["a0"] = a0
+    p["Soil_Properties"]["psi_sat"] = psi_sat
     p["Soil_Properties"]["epsilon"] = 1.0e-7
     p["Water_Content"]["Wilting_Point_cm"] = 1500.0
-    mult = 1.0
     if perturb_theta:
-        p["Water_Content"]["Theta_Max"] = float(rng.uniform(0.25, 0.35))
-        mult = float(np.exp(0.2 * rng.standard_normal()))
+        p["Water_Content"]["Theta_Max"] = theta_max
     if mixed:
-        p["Hydrological_Model"]["Name"] = \
-            ("vrettas_fung", "vanGenuchten")[int(rng.integers(2))]
-        p["Hydrological_Model"]["Porosity_Profile"] = \
-            ("Constant", "Linear", "Exponential", "Stratified")[int(rng.integers(4))]
+        p["Hydrological_Model"]["Name"] = _MODELS[model]
+        p["Hydrological_Model"]["Porosity_Profile"] = _PROFILES[profile]
     return p, mult
+
+
+def ensemble_columns(base_params, first_column, count, mixed=False,
+                     perturb_theta=False, seed=ENSEMBLE_SEED):
+    """The same members as ``ensemble_member`` for the global ids
+    ``first_column .. first_column + count - 1`` in struct-of-arrays form:
+    ``(base, columns)`` where ``base`` is the parameter dict shared by all
+    members (wilting point at +1500) and ``columns`` maps the per-column keys of
+    ``pack.pack_ensemble`` to arrays of length ``count``."""
+    base = copy.deepcopy(base_params)
+    base["Soil_Properties"]["epsilon"] = 1.0e-7
+    base["Water_Content"]["Wilting_Point_cm"] = 1500.0
+    cols = {"n": np.empty(count), "a0": np.empty(count), "psi_sat": np.empty(count),
+            "precip_mult": np.ones(count)}
+    if perturb_theta:
+        cols["Theta_Max"] = np.empty(count)
+    if mixed:
+        cols["model"] = np.empty(count, dtype=object)
+        cols["profile"] = np.empty(count, dtype=object)
+    for k in range(count):
+        n, a0, psi_sat, theta_max, mult, model, profile = \
+            _member_draws(_member_rng(first_column + k, seed), mixed, perturb_theta)
+        cols["n"][k], cols["a0"][k], cols["psi_sat"][k] = n, a0, psi_sat
+        cols["precip_mult"][k] = mult
+        if perturb_theta:
+            cols["Theta_Max"][k] = theta_max
+        if mixed:
+            cols["model"][k], cols["profile"][k] = _MODELS[model], _PROFILES[profile]
+    return base, cols
 
 
 def fine_grid_site(path, max_depth=5000.0):

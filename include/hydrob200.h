@@ -34,7 +34,7 @@ typedef struct hb_ctx hb_ctx;
 /* Library / device management. */
 const char *hb_last_error(void);
 int  hb_version(void);
-/* nx: nodes per column (2 <= nx <= hb_max_nx()); n_cols: columns on this GPU. */
+/* nx: nodes per column (4 <= nx <= hb_max_nx()); n_cols: columns on this GPU. */
 hb_ctx *hb_create(int device, int nx, int n_cols);
 int  hb_destroy(hb_ctx *ctx);
 int  hb_max_nx(void);
@@ -95,17 +95,33 @@ int  hb_spinup(hb_ctx *ctx, int max_iter, const double *nrnd0, const double *zwt
  * every column; row 0 only records the initial diagnostics.  Asynchronous. */
 int  hb_run(hb_ctx *ctx, int w0, int w1);
 
+/* Scheduling of hb_run.  Columns are independent, so the schedule never changes a
+ * result, only the length of the launch: with adaptive != 0 (default) the columns
+ * the previous hb_run on this context found expensive (RHS evaluations well above
+ * the mean) are started first and integrated back to back, the others are time
+ * sliced in chunks of rows; adaptive == 0 keeps the plain chunk-major order. */
+int  hb_set_schedule(hb_ctx *ctx, int adaptive);
+
 /* Results.  wscal[ncol][T][HB_NWSCAL]; fields[ncol][n_out][HB_NFIELD][nx];
- * counters[ncol][HB_NCOUNTER]. */
+ * counters[ncol][HB_NCOUNTER].  The _rows variants read a slice of the rows
+ * (wscal[ncol][nrow][HB_NWSCAL], fields[ncol][nout][HB_NFIELD][nx]) -- the form a
+ * long run integrated slice by slice (hb_run(w0, w1)) reads its results in.  A
+ * getter fails if a kernel raised an error (e.g. a noise tape that is too short). */
 int  hb_get_wscal(hb_ctx *ctx, int col0, int ncol, double *wscal);
+int  hb_get_wscal_rows(hb_ctx *ctx, int col0, int ncol, int row0, int nrow, double *wscal);
 int  hb_get_fields(hb_ctx *ctx, int col0, int ncol, double *fields);
+int  hb_get_fields_rows(hb_ctx *ctx, int col0, int ncol, int out0, int nout, double *fields);
 int  hb_get_counters(hb_ctx *ctx, int col0, int ncol, int64_t *counters);
 int  hb_reset_counters(hb_ctx *ctx);
-/* Ensemble statistics over this context's columns, written to DEVICE buffers
- * (so that the caller can all-reduce them with NCCL): sum and sum of squares
- * of the estimated water-table node index per row, [T] each, and the number of
- * columns that contributed. */
-int  hb_wtd_moments_dev(hb_ctx *ctx, double *sum_dev, double *sumsq_dev);
+/* Ensemble statistics over this context's columns, written to DEVICE buffers (so
+ * that the caller can all-reduce them with NCCL; sums do not depend on the
+ * schedule): per row, the number of columns that contributed (skipped windows do
+ * not), the sum and the sum of squares of the estimated water-table node index
+ * (count_dev, wtd_sum_dev, wtd_sumsq_dev: [T] each; count_dev may be NULL); and,
+ * when theta_sum_dev / theta_sumsq_dev are given ([n_out][nx] each), the same two
+ * moments of the water content theta at every output row and node. */
+int  hb_moments_dev(hb_ctx *ctx, double *count_dev, double *wtd_sum_dev, double *wtd_sumsq_dev,
+                    double *theta_sum_dev, double *theta_sumsq_dev);
 /* Number of this library's kernel launches since hb_create. */
 int64_t hb_launch_count(hb_ctx *ctx);
 /* Diagnostic builds (-DHB_PHASE_TIMING=1) only: cycles thread 0 spent in each
@@ -132,6 +148,13 @@ int  hb_num_jac(hb_ctx *ctx, int col, const double *psi, const double *nrnd, dou
 /* Tridiagonal solve (I - c J) x = b with the in-kernel partition solver. */
 int  hb_tri_solve(hb_ctx *ctx, const double *dl, const double *d, const double *du,
                   double c, const double *b, double *x);
+/* find_wtd(psi >= psi_sat) of column col on the device (utilities.py:56-99). */
+int  hb_find_wtd(hb_ctx *ctx, int col, const double *psi, int32_t *wtd_node);
+/* The n standard normals the PHILOX mode draws for (seed, global column, window):
+ * window >= 1 is the refresh field of that forcing row, 0 the run's base field,
+ * -1 the spin-up field. */
+int  hb_philox_normals(hb_ctx *ctx, uint64_t seed, int64_t global_column, int window, int n,
+                       double *out);
 /* One RichardsPDE.solve (richards_pde.py:478-537) for column col: y0 -> y_end,
  * nrnd is damped in place on failure; stats[HB_NCOUNTER]. */
 int  hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0,
