@@ -97,11 +97,23 @@ class EnsembleSimulation:
         ``first .. first + count - 1`` (e.g. ``synthetic.ensemble_columns``).
         ``rank`` / ``world`` default to the torch.distributed (or torchrun
         environment) values; ``device`` defaults to LOCAL_RANK."""
-        if rank is None or world is None:
-            rank = int(os.environ.get("RANK", "0")) if rank is None else rank
-            world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
+        first, count, base_params, local, ser = cls.local_share(base_params, columns, n_total, rank, world,
+                                                                 series_of_col)
+        sim = cls(name=name, seed=seed, device=device, noise=noise)
+        sim.setupEnsemble(base_params, data, local, first_column=first, series_of_col=ser)
+        sim.n_global = int(n_total)
+        return sim
+
+    @staticmethod
+    def local_share(base_params, columns, n_total, rank=None, world=None, series_of_col=None):
+        """Host-side sharding of `from_global` (no device needed): this rank's block
+        ``(first, count, base_params, local columns, local series map)``."""
+        if rank is None:
+            rank = int(os.environ.get("RANK", "0"))
+        if world is None:
+            world = int(os.environ.get("WORLD_SIZE", "1"))
         first, count = column_range(int(n_total), int(rank), int(world))
         if count < 1:
             raise ValueError(" EnsembleSimulation: this rank has no columns (n_total < world).")
@@ -110,10 +122,7 @@ class EnsembleSimulation:
         else:
             local = {k: np.asarray(v)[first:first + count] for k, v in columns.items()}
         ser = None if series_of_col is None else np.asarray(series_of_col)[first:first + count]
-        sim = cls(name=name, seed=seed, device=device, noise=noise)
-        sim.setupEnsemble(base_params, data, local, first_column=first, series_of_col=ser)
-        sim.n_global = int(n_total)
-        return sim
+        return first, count, base_params, local, ser
 
     def _finish_setup(self, params0, base, par, stat, tables, series_of_col, first_column):
         m = self.mData

@@ -71,3 +71,49 @@ def test_sharded_statistics_match_single_process():
     assert np.array_equal(out["n"], cnt.astype(float))
     assert np.allclose(out["mean"], mean, rtol=1e-13)
     assert np.allclose(out["std"], std, rtol=1e-9)
+
+
+def _share_worker(rank, world, port, n_total, out):
+    """What EnsembleSimulation.from_global does on the host, per rank: take this rank's block of
+    the global ensemble, pack it, and all-reduce a statistic (here: count / sum / sum of squares
+    of the porosity profile, the stand-in for theta without a device)."""
+    from hydromodel_b200 import pack
+    from hydromodel_b200.ensemble import EnsembleSimulation
+    from hydromodel_b200.synthetic import ensemble_columns, synthetic_forcing
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    base = default_params(SITE)
+
+    def members(first, count):
+        return ensemble_columns(base, first, count, perturb_theta=True)
+    first, count, b, cols, _ = EnsembleSimulation.local_share(None, members, n_total)   # rank/world from the env
+    ens = pack.pack_ensemble(b, synthetic_forcing(30), cols)
+    phi = ens["stat"][:, pack.S_PHI_NODE, :]
+    cnt, s, q = (torch.from_numpy(v) for v in local_moments(phi))
+    mean, std, n = reduce_moments(cnt, s, q)
+    ids = torch.tensor([float(first), float(count)])
+    gathered = [torch.zeros(2) for _ in range(world)]
+    dist.all_gather(gathered, ids)
+    if rank == 0:
+        out["mean"], out["std"], out["n"] = mean.numpy().copy(), std.numpy().copy(), n.numpy().copy()
+        out["blocks"] = [tuple(int(v) for v in g.tolist()) for g in gathered]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_from_global_host_sharding_world_size_2():
+    from hydromodel_b200 import pack
+    from hydromodel_b200.synthetic import ensemble_columns, synthetic_forcing
+    n_total = 37
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_share_worker, args=(2, port, n_total, out), nprocs=2, join=True)
+    assert out["blocks"] == [(0, 19), (19, 18)]
+    b, cols = ensemble_columns(default_params(SITE), 0, n_total, perturb_theta=True)
+    phi = pack.pack_ensemble(b, synthetic_forcing(30), cols)["stat"][:, pack.S_PHI_NODE, :]
+    assert np.all(out["n"] == n_total)
+    assert np.allclose(out["mean"], phi.mean(axis=0), rtol=1e-13)
+    assert np.allclose(out["std"], phi.std(axis=0), rtol=1e-6, atol=1e-12)

@@ -134,24 +134,48 @@ def _teacher_forced_gpu(g, prefix, col, spinup, limit=None):
 
 
 def test_windows_default_run_against_reference(golden):
-    """K4+K5 teacher-forced: same bar as the oracle's own test
-    (tests/test_oracle.py::test_windows_default_run_against_reference)."""
-    g = golden("windows_default.npz")
+    """K4+K5 teacher-forced: the 150 taped windows of the default run, each from
+    the reference's own start state.  Windows whose four counters (nfev, njev, nlu, steps) equal
+    the tape took the same decisions: there the end state must agree to rounding level; the
+    fraction of windows with a flipped decision and their error are judged separately.
+
+    The bars come from tests/golden/noise_floor.npz -- the reference against itself with the
+    start state perturbed by 1e-14 relative (make_golden_floor.py): with identical counters the
+    reference's own twin differs by up to `floor_same` (0.042) solver-tolerance units, median
+    8e-6 -- a tighter bar than that is not a property of the algorithm."""
+    g, nf = golden("windows_default.npz"), golden("noise_floor.npz")
     errs, same, wtd_ok = _teacher_forced_gpu(g, "", default_column(), 0)
-    print("gpu windows: counters-match %.3f  err median %.2e  p95 %.2e  max %.2e" %
-          (same.mean(), np.median(errs), np.quantile(errs, 0.95), errs.max()))
-    assert same.mean() >= 0.95
-    assert np.mean(errs <= 0.1) >= 0.95 and errs.max() < 5.0
-    assert np.median(errs) < 1e-4
+    floor_same = nf["tf_units"][nf["tf_same"] == 1].max()
+    floor_flip = 1.0 - nf["tf_same"].mean()
+    print("gpu windows: counters-match %.3f (reference twin %.3f); matching windows: err median %.2e "
+          "max %.2e (reference twin: median %.2e max %.2e); flipped windows: max %.2e" %
+          (same.mean(), nf["tf_same"].mean(), np.median(errs[same]), errs[same].max(),
+           np.median(nf["tf_units"]), floor_same, errs[~same].max() if (~same).any() else 0.0))
+    # windows with the tape's counters: within 3x of what the reference does against itself
+    assert errs[same].max() <= 3.0 * floor_same
+    assert np.median(errs[same]) <= 10.0 * np.median(nf["tf_units"])
+    # decision flips: reported separately; no more frequent than 3x the reference's own rate
+    # (floor 1 / 150), and a flipped window still ends within 5 tolerance units
+    assert (1.0 - same.mean()) <= max(3.0 * floor_flip, 0.03)
+    assert errs.max() < 5.0
     assert wtd_ok.all()
 
 
 def test_windows_spinup_against_reference(golden):
-    g = golden("spinup_default.npz")
+    """Spin-up windows (SPINUP flags, saturated start: the stiffest regime), teacher-forced.
+    The reference's own twin (noise_floor.npz: start state x (1 + 1e-14)) keeps its counters in
+    81 % of these windows and moves the end state by up to 31 tolerance units when a decision
+    flips; the bars are those figures with a margin, not hand-set numbers."""
+    g, nf = golden("spinup_default.npz"), golden("noise_floor.npz")
     errs, same, wtd_ok = _teacher_forced_gpu(g, "", default_column(), 1)
-    print("gpu spinup windows: counters-match %.3f  err median %.2e max %.2e" %
-          (same.mean(), np.median(errs), errs.max()))
-    assert same.mean() >= 0.75
+    print("gpu spinup windows: counters-match %.3f (reference twin %.3f)  err median %.2e max %.2e "
+          "(reference twin max %.2e); matching windows max %.2e" %
+          (same.mean(), nf["spin_same"].mean(), np.median(errs), errs.max(), nf["spin_units"].max(),
+           errs[same].max()))
+    assert same.mean() >= nf["spin_same"].mean() - 0.1
+    assert errs.max() <= 1.5 * nf["spin_units"].max()
+    floor_same = nf["spin_units"][nf["spin_same"] == 1].max()
+    assert errs[same].max() <= 3.0 * floor_same
     assert np.median(errs) < 1e-2
     assert wtd_ok.mean() >= 0.9
 
@@ -194,12 +218,13 @@ def test_free_running_ensemble_against_reference_and_oracle(golden):
     """hb_run on an ensemble of identical columns (host noise tape): every
     column must reproduce the oracle's free-running loop, and the reference's
     recorded run, over 60 windows.  Free-running trajectories of this
-    integrator diverge at the reference's own noise floor (a 1e-14 perturbation
-    of the reference's initial state moves theta by 2e-5 and psi by 2e-3
-    relative within 120 windows), hence the free-running
-    protocol of SURVEY section 8(c).4: water-table node identical, psi within
-    2e-2 relative (20 solver-tolerance units), theta within 2e-4 relative."""
-    g = golden("windows_default.npz")
+    integrator diverge at the reference's own noise floor: tests/golden/noise_floor.npz
+    holds two reference runs from IC and IC x (1 + 1e-12) with the same noise (the
+    device's RHS differs from the reference's by ~1e-12 relative, see the RHS test):
+    within these 60 windows they drift apart by `free_e12_units` tolerance units in psi
+    and `free_e12_theta_rel` in theta.  The bars are 2x those figures (SURVEY 8c.4:
+    water-table node identical, psi ~2e-2 relative, theta ~2e-4 relative)."""
+    g, nf = golden("windows_default.npz"), golden("noise_floor.npz")
     col = default_column()
     f = col["forcing"]
     T, C = 61, 8
@@ -224,12 +249,16 @@ def test_free_running_ensemble_against_reference_and_oracle(golden):
     for ref_idx in (g["wtd_est_cm"][:T] / 5.0, o_wscal[:, pack.W_WTD_EST]):
         diff = np.abs(wscal[0, :, pack.W_WTD_EST] - ref_idx)
         assert diff.max() <= 1 and np.mean(diff == 0) >= 0.95
-    assert tol_scaled(psi[0], g["psi_press"][T - 1]) < 20.0
-    assert tol_scaled(psi[0], o_psi) < 20.0
+    psi_bar = 2.0 * max(nf["free_e12_units"][:T].max(), nf["free_e14_units"][:T].max())
+    theta_bar = 2.0 * max(nf["free_e12_theta_rel"][:T].max(), nf["free_e14_theta_rel"][:T].max())
+    print("free-running bars from the reference's own twins: psi %.2f units, theta %.2e relative; "
+          "device vs reference: psi %.2f units" % (psi_bar, theta_bar, tol_scaled(psi[0], g["psi_press"][T - 1])))
+    assert tol_scaled(psi[0], g["psi_press"][T - 1]) < psi_bar
+    assert tol_scaled(psi[0], o_psi) < psi_bar
     assert fields.shape == (C, 7, 4, 401)
     for o, row in enumerate(range(0, T, 10)):
-        assert np.allclose(fields[0, o, pack.F_THETA], g["theta_vol"][row], rtol=2e-4)
-        assert np.allclose(fields[0, o, pack.F_KBKG], g["K_bkg"][row], rtol=2e-4)
+        assert np.allclose(fields[0, o, pack.F_THETA], g["theta_vol"][row], rtol=theta_bar)
+        assert np.allclose(fields[0, o, pack.F_KBKG], g["K_bkg"][row], rtol=max(theta_bar, 2e-4))
     assert np.allclose(wscal[0, 1:, pack.W_LATERAL], g["out_lateral_flow"][:T - 1], rtol=1e-3, atol=1e-9)
     assert counters[0, pack.C_NWINDOWS] == T - 1
     assert abs(counters[0, pack.C_NFEV] - o_stats[pack.C_NFEV]) <= 0.05 * o_stats[pack.C_NFEV]
@@ -251,9 +280,13 @@ def test_spinup_kernel_against_oracle(golden):
     nr = g["n_rnd"][0]
     psi_sat = col["par"][pack.P_PSI_SAT]
     ctx.set_forcing(f["precipitation_cm"], f["wtd_idx"], f["daylight"], f["atm"])
-    # (the first window from the saturated column is the most rounding-sensitive
-    # one of the whole tape: the reference-vs-oracle pair differs by ~20 units there)
-    for start, n_it, tol in ((psi0, 1, 30.0), (g["y0"][-6], 3, 20.0)):
+    # bars from the reference against itself (noise_floor.npz: spin-up solves from a start state
+    # perturbed by 1e-14): early solves from the saturated column flip decisions and then move by
+    # up to spin_units[:8].max() tolerance units, late ones by spin_units[-8:].max()
+    nf = golden("noise_floor.npz")
+    tol_early = 1.5 * nf["spin_units"][:8].max()
+    tol_late = max(1.5 * nf["spin_units"][-8:].max(), 3.0 * nf["tf_units"].max())
+    for start, n_it, tol in ((psi0, 1, tol_early), (g["y0"][-6], 3, tol_late)):
         ctx.set_state(np.tile(start, (2, 1)))
         iters = ctx.spinup(f["zWtd_cm"][0], np.tile(nr, (2, 1)), max_iter=n_it)
         psi = ctx.get_state()

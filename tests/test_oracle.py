@@ -14,16 +14,13 @@ from helpers import (column_from_json, default_column, rhs_cases, rhs_configs, t
 def test_find_wtd_reference_vectors():
     """The four exact vectors of the reference's own test
     (code/tests/test_utilities.py:56-86): expected 9, 0, 6, 7."""
-    a = np.ones(10, dtype=bool); a[:9] = False          # dry above the last cell
-    assert oracle.find_wtd(np.r_[np.zeros(9, bool), True]) == 9
-    assert oracle.find_wtd(np.ones(10, bool)) == 0
-    v = np.array([0, 0, 1, 0, 1, 0, 1, 1, 1, 1], dtype=bool)
-    assert oracle.find_wtd(v) == 6
-    v = np.array([1, 1, 1, 0, 1, 1, 0, 1, 1, 1], dtype=bool)
-    assert oracle.find_wtd(v) == 7
     from hydromodel_b200.src.utilities import find_wtd
-    for vec in (np.r_[np.zeros(9, bool), True], np.ones(10, bool), v):
-        assert find_wtd(vec) == oracle.find_wtd(vec)
+    cases = (([0] * 10, 9), ([1] * 10, 0), ([0, 0, 0, 0, 0, 0, 1, 1, 1, 1], 6),
+             ([0, 1, 0, 1, 0, 0, 0, 1, 1, 1], 7))
+    for vec, want in cases:
+        v = np.array(vec, dtype=bool)
+        assert oracle.find_wtd(v) == want
+        assert find_wtd(v) == want
 
 
 def test_fd_colouring_matches_scipy(golden):
