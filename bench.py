@@ -294,6 +294,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spinup", action="store_true", help="skip the separately timed batched spin-up")
     ap.add_argument("--no-adaptive", action="store_true", help="plain chunk-major schedule")
+    ap.add_argument("--fast", action="store_true",
+                    help="fast mode (SURVEY 8f.4, NOT the reference's arithmetic): warm-started windows + "
+                         "3-colour Jacobian; a second bench line, never the headline")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -419,6 +422,9 @@ def main():
     ctx.set_grid(wl["x"], grp, ng)
     if a.no_adaptive:
         ctx.set_schedule(False)
+    if a.fast:
+        ctx.set_fast_mode(warm=True, jac3=True)
+        config["mode"] = "FAST (hb_set_fast_mode: warm-started windows, 3-colour FD Jacobian) -- not parity mode"
 
     def upload():
         """Host -> device copies of one step: statics, forcing, (tape), state."""

@@ -14,6 +14,8 @@ import numpy as np
 from . import build as _build
 from .pack import NPARAM, NSTATIC, NWSCAL, NFIELD, NCOUNTER
 
+FAST_WARM, FAST_JAC3 = 1, 2          # include/hb_layout.h HB_FAST_*
+
 _lib = None
 
 _D = ct.POINTER(ct.c_double)
@@ -42,6 +44,7 @@ EXPORTS = {
     "hb_spinup": (ct.c_int, [ct.c_void_p, ct.c_int, _D, _D, _I]),
     "hb_run": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int]),
     "hb_set_schedule": (ct.c_int, [ct.c_void_p, ct.c_int]),
+    "hb_set_fast_mode": (ct.c_int, [ct.c_void_p, ct.c_int]),
     "hb_get_wscal": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, _D]),
     "hb_get_wscal_rows": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, _D]),
     "hb_get_fields": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, _D]),
@@ -63,7 +66,7 @@ EXPORTS = {
     "hb_philox_normals": (ct.c_int, [ct.c_void_p, ct.c_uint64, ct.c_int64, ct.c_int, ct.c_int, _D]),
     "hb_solve_window": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_double, ct.c_double, _D, _D,
                                    ct.c_double, ct.c_int, ct.c_int, ct.c_int, ct.c_double, _D, _L,
-                                   _D, _D, ct.POINTER(ct.c_int)]),
+                                   _D, _D, ct.POINTER(ct.c_int), _D]),
 }
 
 COUNTER_NAMES = ("nfev", "njev", "nlu", "nsteps", "nreject", "nfail", "nrhs", "nnewton",
@@ -241,6 +244,10 @@ class Context:
     def run(self, w0=0, w1=None):
         self._ck(self.lib.hb_run(self._h, int(w0), int(self.T if w1 is None else w1)))
 
+    def set_fast_mode(self, warm=True, jac3=True):
+        """Fast mode of ``run`` (never the default): see HB_FAST_* in include/hb_layout.h."""
+        self._ck(self.lib.hb_set_fast_mode(self._h, (FAST_WARM if warm else 0) | (FAST_JAC3 if jac3 else 0)))
+
     def set_schedule(self, adaptive=True):
         self._ck(self.lib.hb_set_schedule(self._h, int(bool(adaptive))))
 
@@ -351,9 +358,12 @@ class Context:
         stats = np.zeros(NCOUNTER, dtype=np.int64)
         lat, tr = ct.c_double(0.0), ct.c_double(0.0)
         status = ct.c_int(0)
+        t_acc = np.zeros(self.nx)
         self._ck(self.lib.hb_solve_window(self._h, col, float(t0), float(t1), _d(y0), _d(nrnd),
                                           float(precip), int(wtd), int(daylight), int(spinup),
                                           float(atm), _d(y_end), stats.ctypes.data_as(_L),
-                                          ct.byref(lat), ct.byref(tr), ct.byref(status)))
+                                          ct.byref(lat), ct.byref(tr), ct.byref(status), _d(t_acc)))
         self.last_transpiration = tr.value
+        # accepted step times of the last attempt (sol.t[1:] of scipy), for decision-level parity
+        self.last_t_accepted = t_acc[:min(int(stats[3]), self.nx)].copy()
         return y_end, dict(zip(COUNTER_NAMES, stats.tolist())), status.value, lat.value

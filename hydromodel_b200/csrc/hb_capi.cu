@@ -190,6 +190,7 @@ struct hb_ctx {
     bool adaptive = true;   // run_kernel launch plan from the previous launch's per-column cost
     bool have_cost = false; // a previous hb_run left per-column costs on the device
     int fast_flags = 0;     // HB_FAST_* (fast mode, never the default)
+    int *grp3 = nullptr;    // colouring j mod 3 of the tridiagonal pattern (fast mode)
 };
 
 template <typename T>
@@ -280,6 +281,12 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
         }                                                           \
     } while (0)
 
+#define DISPATCH_RUN(ctx, FAST_, grid, ...)                                                   \
+    do {                                                                                      \
+        HB_FOR_VARIANT(ctx, (K::run_kernel<NT_, CPT_, MB_, FL_, FAST_><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
+        (ctx)->launches++;                                                                    \
+    } while (0)
+
 #define DISPATCH(ctx, NAME, grid, ...)                                                        \
     do {                                                                                      \
         HB_FOR_VARIANT(ctx, (K::NAME<NT_, CPT_, MB_, FL_><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
@@ -355,6 +362,15 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     d.psi = psi; d.noise_base = nb; d.queue = queue; d.slot_next = slot; d.counters = cnt;
     d.done = done; d.chunk = 16;
     d.credit = credit; d.order = order; d.n_hot = nhot; d.err_flags = errf; d.cost = cost;
+    d.t_acc = nullptr;
+    {
+        std::vector<int> g3(nx);
+        for (int k = 0; k < nx; ++k) g3[k] = k % 3;
+        if (dev_alloc(ctx, &ctx->grp3, nx) ||
+            cudaMemcpy(ctx->grp3, g3.data(), nx * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            fail("hb_create: colouring upload failed"); hb_destroy(ctx); return nullptr;
+        }
+    }
     if (tuning_env("HB_NO_ADAPTIVE")) ctx->adaptive = false;
     { long long *pc; if (dev_alloc(ctx, &pc, 16)) { hb_destroy(ctx); return nullptr; } d.phase_cycles = pc; }
     if (const char *v = tuning_env("HB_CHUNK")) { const int w = atoi(v); if (w > 0) d.chunk = w; }
@@ -366,7 +382,8 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     HB_FOR_VARIANT(ctx, {
         rc = prep_kernel(ctx, K::hook_kernel<NT_, CPT_, MB_, FL_>, NT_);
         if (!rc) rc = prep_kernel(ctx, K::spinup_kernel<NT_, CPT_, MB_, FL_>, NT_);
-        if (!rc) rc = prep_kernel(ctx, K::run_kernel<NT_, CPT_, MB_, FL_>, NT_);
+        if (!rc) rc = prep_kernel(ctx, K::run_kernel<NT_, CPT_, MB_, FL_, true>, NT_);
+        if (!rc) rc = prep_kernel(ctx, K::run_kernel<NT_, CPT_, MB_, FL_, false>, NT_);
     });
     if (rc) { hb_destroy(ctx); return nullptr; }
     {   // per-CTA global scratch of the resident CTAs (difference table, step factors, ET vectors)
@@ -676,7 +693,13 @@ int hb_run(hb_ctx *ctx, int w0, int w1)
         k.order = nullptr;
         CK(cudaMemsetAsync(d.cost, 0, (size_t)d.n_cols * sizeof(long long), ctx->stream));
     }
-    DISPATCH(ctx, run_kernel, grid, k, w0, w1);
+    if (ctx->fast_flags) {
+        // fast mode (never the default): warm-started windows, 3-colour Jacobian without retry pass
+        if (ctx->fast_flags & HB_FAST_JAC3) { k.grp = ctx->grp3; k.ng = 3; }
+        DISPATCH_RUN(ctx, true, grid, k, w0, w1);
+    } else {
+        DISPATCH_RUN(ctx, false, grid, k, w0, w1);
+    }
     CK(cudaGetLastError());
     ctx->have_cost = true;
     return 0;
@@ -741,6 +764,14 @@ int hb_reset_counters(hb_ctx *ctx)
     if (!ctx) return fail("null ctx");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d.counters, 0, (size_t)ctx->d.n_cols * HB_NCOUNTER * sizeof(long long), ctx->stream));
+    return 0;
+}
+
+int hb_set_fast_mode(hb_ctx *ctx, int flags)
+{
+    if (!ctx) return fail("null ctx");
+    if (flags & ~(HB_FAST_WARM | HB_FAST_JAC3)) return fail("hb_set_fast_mode: unknown flag");
+    ctx->fast_flags = flags;
     return 0;
 }
 
@@ -830,7 +861,9 @@ double hb_measure_fp64_peak(hb_ctx *ctx)
 static int run_hook(hb_ctx *ctx, HookArgs h)
 {
     h.io = ctx->hook_io; h.stats = ctx->hook_stats;
-    DISPATCH(ctx, hook_kernel, 1, ctx->d, h);
+    DevCtx k = ctx->d;
+    if (h.mode == HK_WINDOW) k.t_acc = ctx->hook_io + (size_t)7 * ctx->d.nx;     // accepted step times
+    DISPATCH(ctx, hook_kernel, 1, k, h);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
@@ -944,7 +977,8 @@ int hb_philox_normals(hb_ctx *ctx, uint64_t seed, int64_t global_column, int win
 
 int hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0, double *nrnd,
                     double precip, int wtd, int daylight, int spinup, double atm, double *y_end,
-                    int64_t *stats, double *lateral_flow, double *transpiration, int *status)
+                    int64_t *stats, double *lateral_flow, double *transpiration, int *status,
+                    double *t_accepted)
 {
     if (ready(ctx) || range_ok(ctx, col, 1)) return -1;
     CK(cudaSetDevice(ctx->device));
@@ -965,6 +999,10 @@ int hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0
     CK(cudaMemcpy(st, ctx->hook_stats, sizeof(st), cudaMemcpyDeviceToHost));
     if (stats) for (int k = 0; k < HB_NCOUNTER; ++k) stats[k] = st[k];
     if (status) *status = (int)st[HB_NCOUNTER];
+    if (t_accepted) {                       // accepted step times of the LAST attempt (sol.t[1:])
+        const long long n = st[HB_C_NSTEPS] < ctx->d.nx ? st[HB_C_NSTEPS] : ctx->d.nx;
+        if (n > 0 && hook_out(ctx, 7, t_accepted, (int)n)) return -1;
+    }
     return 0;
 }
 

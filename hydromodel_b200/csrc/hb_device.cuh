@@ -64,6 +64,7 @@ struct DevCtx {
     int *order;              // [n_cols] launch plan: hot columns first (plan_kernel), or null
     int *n_hot;              // [1] number of hot columns in `order`
     long long *cost;         // [n_cols] RHS evaluations per column in the current launch (next plan)
+    double *t_acc;           // test hook only: accepted step times of the current solve ([nx]), else null
     int *err_flags;          // [1] HB_ERR_* bits raised by kernels, checked by hb_sync / hb_get_*
     int chunk;               // windows per work item of run_kernel
     int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice

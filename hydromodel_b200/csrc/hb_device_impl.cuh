@@ -952,9 +952,17 @@ __device__ __forceinline__ void column_stats(const double *fb, const double *fn,
 //   V_JL/V_JD/V_JU un-normalised column differences J[j-1][j], J[j][j], J[j+1][j]
 //   V_PSI max |difference|           V_SCL its scale       V_DD "too small" flag
 // ---------------------------------------------------------------------------
-template <int NT, int CPT, bool FULL>
+// Fast mode only (never the default): what one window hands to the next
+// one of the same column inside a chunk of rows.
+struct Warm {
+    double h;        // step size the controller proposed after the last accepted step (0: none)
+    bool have_J;     // V_JL/V_JD/V_JU hold a Jacobian of this column (possibly of an earlier window)
+    bool have_fac;   // the finite-difference step factors of this column are in the scratch row
+};
+
+template <int NT, int CPT, bool FULL, bool FAST = false>
 __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
-                                        const double *y_glob, int jac_only = 0)
+                                        const double *y_glob, int jac_only = 0, Warm *warm = nullptr)
 {
     // jac_only (test hook): 1 = return after the initial Jacobian, 2 = the same
     // but starting from the step factors already in the G_FAC scratch row.
@@ -1109,7 +1117,10 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     n_equal++;
                     t = t_new;
                     h_abs = h_loc;
-                    if (tid == 0) cnt[K_NSTEPS]++;
+                    if (tid == 0) {
+                        if (c.t_acc && cnt[K_NSTEPS] < nx) c.t_acc[cnt[K_NSTEPS]] = t_new;     // hb_solve_window hook
+                        cnt[K_NSTEPS]++;
+                    }
                     const bool decide = (n_equal >= order + 1);
 #if HB_DUP_PROBE
                     if (c.dbg & 1024) { double *s2 = HB_GROW(c, G_SK);
@@ -1159,6 +1170,22 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     }
                     go = GO_STEP_BEGIN;
                 }
+            }
+        } else if (FAST && state == S_F0 && warm->h > 0.0) {
+            // ---- fast mode, warm start: no select_initial_step; the first step is the one
+            // the controller proposed at the end of the previous window of this column, and
+            // the Jacobian of that window is kept until a Newton iteration fails to converge
+            // (bdf.py:375-380 then refreshes it).  Order restarts at 1 as in a new solver.
+            h_abs = fmin(warm->h, fabs(wa[WA_TBOUND] - wa[WA_T0]));
+            if (warm->have_J) {
+                for (int i = tid; i < nx; i += NT) D[nxp + i] = b[i] * h_abs;         // D[1] = f0 * h
+                order = 1; n_equal = 0; t = wa[WA_T0];
+                lu_valid = false;
+                go = GO_STEP_BEGIN;
+            } else {
+                for (int i = tid; i < nx; i += NT) { const double f0 = b[i]; D[nxp + i] = f0; ybv[i] = D[i]; fbv[i] = f0; }
+                jac_first = !warm->have_fac; jac_init = true;
+                jb_now = true;
             }
         } else if (state == S_F0) {
             // ---- select_initial_step, first half (common.py:105-115) ----------
@@ -1224,7 +1251,8 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
             int next_state = state, next_g = jac_g + 1;
             bool done = false;
             if (state == S_JG && next_g >= c.ng) { next_state = S_JR; next_g = 0; }
-            if (next_state == S_JR) {
+            if (FAST && next_state == S_JR) done = true;       // fast mode: no 10x-step retry pass
+            else if (next_state == S_JR) {
                 int want = c.ng;
                 for (int j = tid; j < nx; j += NT)
                     if (vd[j] != 0.0 && c.grp[j] >= next_g) want = min(want, c.grp[j]);
@@ -1299,7 +1327,11 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         }
         if (go == GO_STEP_BEGIN) {
             // ---- driver loop / top of _step_impl (ivp.py:659, bdf.py:318-333) --
-            if (t == wa[WA_TBOUND]) { __syncthreads(); return 0; }
+            if (t == wa[WA_TBOUND]) {
+                if (FAST) { warm->h = h_abs; warm->have_J = true; warm->have_fac = true; }
+                __syncthreads();
+                return 0;
+            }
             min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
             if (h_abs < min_step) {
                 h_loc = min_step;
@@ -1316,6 +1348,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                 __syncthreads();
                 for (int i = tid; i < nx; i += NT) y[i] = D[i];
                 __syncthreads();
+                if (FAST) { warm->h = 0.0; warm->have_J = false; }
                 return -1;
             }
             t_new = t + h_loc;
@@ -1370,15 +1403,15 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
 // RichardsPDE.solve (richards_pde.py:478-537): up to 5 attempts, the noise
 // field damped in place by 0.8 after each failure (quirk Q4); the state of the
 // last attempt is left in V_Y (quirk Q5).  Returns 0 ok / 1 failed.
-template <int NT, int CPT, bool FULL>
+template <int NT, int CPT, bool FULL, bool FAST = false>
 __device__ inline int solve_window(const DevCtx &c, int col, const Args &a, double t0, double t1,
-                                   const double *y_glob, bool &noise_damped)
+                                   const double *y_glob, bool &noise_damped, Warm *warm = nullptr)
 {
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     int trials = HB_N_TRIALS, status = 0;
     set_window_args<NV>(c, a, t0, t1);
     while (trials > 0) {
-        status = bdf_attempt<NT, CPT, FULL>(c, col, y_glob);
+        status = bdf_attempt<NT, CPT, FULL, FAST>(c, col, y_glob, 0, warm);
         if (status == 0) break;
         for (int i = threadIdx.x; i < c.nx; i += NT) HB_VEC(c, V_NR)[i] *= HB_NOISE_DAMP;
         noise_damped = true;

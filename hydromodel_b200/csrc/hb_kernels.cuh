@@ -74,7 +74,7 @@ __device__ inline void write_row(const DevCtx &c, int &parity, int col, int row,
 // The chunks of a column are integrated in row order by one owner at a time; state,
 // base noise field and tape position are handed over through global memory
 // (release: __threadfence + atomic on the credit; acquire: the atomic + L2 loads).
-template <int NT, int CPT, int MB, bool FULL>
+template <int NT, int CPT, int MB, bool FULL, bool FAST = false>
 __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ DevCtx c, int w0, int w1)
 {
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
             for (int i = tid; i < nx; i += NT) { nr[i] = __ldcg(nb + i); y[i] = __ldcg(psi_g + i); }
             bool nr_is_base = true;
             long long windows = 0;
+            Warm warm = {0.0, false, false};       // fast mode: nothing is carried into a chunk
             __syncthreads();
             for (int row = r0; row < r1; ++row) {
                 int status = 0;
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
                         a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
                         a.atm = c.atm ? c.atm[(size_t)ser * c.T + row] : 0.0;
                         bool damped = false;
-                        status = solve_window<NT, CPT, FULL>(c, col, a, (double)(row - 1), (double)row, psi_g, damped);
+                        status = solve_window<NT, CPT, FULL, FAST>(c, col, a, (double)(row - 1), (double)row, psi_g,
+                                                                   damped, &warm);
                         if (damped && nr_is_base)
                             for (int i = tid; i < nx; i += NT) __stcg(nb + i, nr[i]);
                         for (int i = tid; i < nx; i += NT) __stcg(psi_g + i, y[i]);
@@ -295,6 +297,8 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
         const int w = find_wtd_nodes<NT, NV>(c, parity, y);
         if (tid == 0) h.stats[0] = w;
     } else if (h.mode == HK_WINDOW) {
+        if (tid < 8) reinterpret_cast<long long *>(HB_XA(c, NV, X_CNT))[tid] = 0;
+        __syncthreads();
         bool damped = false;
         const int st = solve_window<NT, CPT, FULL>(c, h.col, a, h.t0, h.t1, io, damped);
         for (int i = tid; i < nx; i += NT) { io[2 * nx + i] = y[i]; io[nx + i] = nr[i]; }

@@ -101,6 +101,18 @@ enum {                       /* output field ids for hb_get_field           */
 #define HB_NOISE_TAPE    0   /* host-generated N(0,1) vectors (parity mode)  */
 #define HB_NOISE_PHILOX  1   /* on-device Philox4x32-10 + Box-Muller         */
 
+/* Fast mode (hb_set_fast_mode; never the default -- results then differ from the
+ * reference's arithmetic within the integrator's own tolerance).
+ * Either flag selects the fast build of the window loop. */
+#define HB_FAST_WARM     1   /* windows of a column inside a chunk of rows are warm-started:
+                              * first step = the step size proposed at the end of the previous
+                              * window (no select_initial_step, scipy common.py:63-134), Jacobian
+                              * and its step factors carried over until Newton fails to converge
+                              * (scipy builds a new Jacobian at every solve_ivp call, bdf.py:198-241) */
+#define HB_FAST_JAC3     2   /* finite-difference Jacobian with the 3 colours j mod 3 instead of
+                              * scipy's 5 groups, and without the 10x-step retry pass
+                              * (common.py:268-455, _numdiff.py:227-284) */
+
 /* integrator constants, scipy/integrate/_ivp/bdf.py:12-15,244-247 */
 #define HB_MAX_ORDER       5
 #define HB_NEWTON_MAXITER  4

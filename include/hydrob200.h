@@ -95,6 +95,11 @@ int  hb_spinup(hb_ctx *ctx, int max_iter, const double *nrnd0, const double *zwt
  * every column; row 0 only records the initial diagnostics.  Asynchronous. */
 int  hb_run(hb_ctx *ctx, int w0, int w1);
 
+/* Fast mode of hb_run: flags = OR of HB_FAST_* (hb_layout.h), 0 (default) = the reference's
+ * arithmetic.  Departs from scipy common.py:63-134,268-455 and bdf.py:198-241 as the flag
+ * comments say; hb_spinup and the hooks always run the parity path. */
+int  hb_set_fast_mode(hb_ctx *ctx, int flags);
+
 /* Scheduling of hb_run.  Columns are independent, so the schedule never changes a
  * result, only the length of the launch: with adaptive != 0 (default) the columns
  * the previous hb_run on this context found expensive (RHS evaluations well above
@@ -156,11 +161,13 @@ int  hb_find_wtd(hb_ctx *ctx, int col, const double *psi, int32_t *wtd_node);
 int  hb_philox_normals(hb_ctx *ctx, uint64_t seed, int64_t global_column, int window, int n,
                        double *out);
 /* One RichardsPDE.solve (richards_pde.py:478-537) for column col: y0 -> y_end,
- * nrnd is damped in place on failure; stats[HB_NCOUNTER]. */
+ * nrnd is damped in place on failure; stats[HB_NCOUNTER]; t_accepted (may be NULL,
+ * else room for nx values) receives the accepted step times sol.t[1:] of the last
+ * solve_ivp attempt. */
 int  hb_solve_window(hb_ctx *ctx, int col, double t0, double t1, const double *y0,
                      double *nrnd, double precip, int wtd, int daylight, int spinup, double atm,
                      double *y_end, int64_t *stats, double *lateral_flow, double *transpiration,
-                     int *status);
+                     int *status, double *t_accepted);
 
 #ifdef __cplusplus
 }

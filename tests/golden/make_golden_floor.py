@@ -15,7 +15,10 @@ Recorded (reference @ container stack, see make_golden.py):
             (simulation.py:576-649): for each window the reference's own solve and
             a second solve_ivp call from y0 * (1 + eps), eps = 1e-14: end-state
             difference in solver-tolerance units, theta relative difference,
-            whether the four counters agree, water-table node difference.
+            whether the four counters agree (`same`), whether in addition the
+            accepted time grids coincide (`grid`: same decisions), water-table node
+            difference; `*_e12`: the same for four random perturbation patterns of
+            size 1e-12 (the size of the device's rounding differences in the RHS).
   spin_*    the same for the first 24 and last 8 solves of the spin-up
             (simulation.py:444-480) -- the saturated start is the stiffest regime.
   free_*    free-running twins: two reference runs of 150 windows from IC and
@@ -44,14 +47,32 @@ def _units(y, ref):
     return float(np.max(np.abs(y - ref) / (1e-3 + 1e-3 * np.abs(ref))))
 
 
+_RNG = np.random.default_rng(4321)
+N_E12 = 4          # random 1e-12 perturbation patterns per solve
+
+
+def _same(a, b):
+    """Same decisions: the four counters agree AND the accepted time grids coincide."""
+    counters = (a.nfev, a.njev, a.nlu, a.t.size) == (b.nfev, b.njev, b.nlu, b.t.size)
+    grid = counters and bool(np.allclose(a.t, b.t, rtol=1e-6, atol=1e-9))
+    return int(counters), int(grid)
+
+
 def _twin_solve_ivp(fun, t_span, y0, **kw):
-    """The reference's call, preceded by the same call from a perturbed start."""
-    twin = _real(fun, t_span=t_span, y0=np.asarray(y0, dtype=float) * (1.0 + EPS), **kw)
+    """The reference's call, preceded by the same call from perturbed starts: y0 * (1 + 1e-14)
+    and N_E12 random patterns y0 * (1 + 1e-12 * N(0,1)) -- the size of the device's and the
+    oracle's rounding differences in the right-hand side (1e-12 relative, RHS parity test)."""
+    y0 = np.asarray(y0, dtype=float)
+    twin = _real(fun, t_span=t_span, y0=y0 * (1.0 + EPS), **kw)
+    twins12 = [_real(fun, t_span=t_span, y0=y0 * (1.0 + 1e-12 * _RNG.standard_normal(y0.size)), **kw)
+               for _ in range(N_E12)]
     sol = _real(fun, t_span=t_span, y0=y0, **kw)
-    _TWIN.append({"units": _units(twin.y[:, -1], sol.y[:, -1]),
-                  "same": int((twin.nfev, twin.njev, twin.nlu, twin.t.size) ==
-                              (sol.nfev, sol.njev, sol.nlu, sol.t.size)),
-                  "y_end": sol.y[:, -1].copy(), "y_twin": twin.y[:, -1].copy()})
+    c14, g14 = _same(twin, sol)
+    rec = {"units": _units(twin.y[:, -1], sol.y[:, -1]), "same": c14, "grid": g14,
+           "y_end": sol.y[:, -1].copy(), "y_twin": twin.y[:, -1].copy(),
+           "units12": [_units(t.y[:, -1], sol.y[:, -1]) for t in twins12],
+           "same12": [_same(t, sol)[0] for t in twins12], "grid12": [_same(t, sol)[1] for t in twins12]}
+    _TWIN.append(rec)
     return sol
 
 
@@ -81,6 +102,10 @@ def main(n_windows=150):
     zeros = np.zeros(sim.mData["z_grid"].size)
     blob["spin_units"] = np.array([r["units"] for r in keep])
     blob["spin_same"] = np.array([r["same"] for r in keep])
+    blob["spin_grid"] = np.array([r["grid"] for r in keep])
+    blob["spin_units_e12"] = np.array([r["units12"] for r in keep])
+    blob["spin_same_e12"] = np.array([r["same12"] for r in keep])
+    blob["spin_grid_e12"] = np.array([r["grid12"] for r in keep])
     blob["spin_wtd_diff"] = np.array([abs(_wtd(sim, r["y_end"]) - _wtd(sim, r["y_twin"])) for r in keep])
     blob["spin_n_solves"] = np.array(len(spin))
     print(f"  spin-up twins: {len(spin)} solves; kept units {blob['spin_units'].round(3)}")
@@ -90,6 +115,10 @@ def main(n_windows=150):
     tf = list(_TWIN)
     blob["tf_units"] = np.array([r["units"] for r in tf])
     blob["tf_same"] = np.array([r["same"] for r in tf])
+    blob["tf_grid"] = np.array([r["grid"] for r in tf])
+    blob["tf_units_e12"] = np.array([r["units12"] for r in tf])
+    blob["tf_same_e12"] = np.array([r["same12"] for r in tf])
+    blob["tf_grid_e12"] = np.array([r["grid12"] for r in tf])
     blob["tf_theta_rel"] = np.array([_theta_rel(sim, r["y_end"], r["y_twin"], zeros) for r in tf])
     blob["tf_wtd_diff"] = np.array([abs(_wtd(sim, r["y_end"]) - _wtd(sim, r["y_twin"])) for r in tf])
     ic = np.array(sim.mData["initial_cond"], dtype=float)

@@ -112,10 +112,14 @@ def test_num_jac_against_scipy_and_oracle(golden):
     ctx.close()
 
 
-def _teacher_forced_gpu(g, prefix, col, spinup, limit=None):
+def _teacher_forced_gpu(g, prefix, col, spinup, limit=None, with_grid=False):
+    """Every taped window from the reference's own start state.  `same`: the four counters equal
+    the tape's; `grid`: in addition the accepted step times coincide with the reference's sol.t
+    (rtol 1e-6) -- the solver took the same decisions."""
     ctx, grp = make_ctx(col)
     n = g[prefix + "y0"].shape[0] if limit is None else min(limit, g[prefix + "y0"].shape[0])
-    errs, same, wtd_ok, o_errs = [], [], [], []
+    errs, same, wtd_ok, grid = [], [], [], []
+    off = g[prefix + "t_acc_off"]
     psi_sat = col["par"][pack.P_PSI_SAT]
     for w in range(n):
         nr = g[prefix + "n_rnd"][w].copy()
@@ -128,55 +132,74 @@ def _teacher_forced_gpu(g, prefix, col, spinup, limit=None):
         errs.append(tol_scaled(y, ref))
         same.append(st["nfev"] == g[prefix + "nfev"][w] and st["njev"] == g[prefix + "njev"][w]
                     and st["nlu"] == g[prefix + "nlu"][w] and st["nsteps"] == g[prefix + "nsteps"][w])
+        ref_t = g[prefix + "t_acc"][off[w] + 1:off[w + 1]]
+        grid.append(bool(same[-1]) and ref_t.size == ctx.last_t_accepted.size and
+                    bool(np.allclose(ctx.last_t_accepted, ref_t, rtol=1e-6, atol=1e-9)))
         wtd_ok.append(oracle.find_wtd(y >= psi_sat) == oracle.find_wtd(ref >= psi_sat))
     ctx.close()
+    if with_grid:
+        return np.array(errs), np.array(same), np.array(wtd_ok), np.array(grid)
     return np.array(errs), np.array(same), np.array(wtd_ok)
+
+
+def _twin_stats(nf, prefix):
+    """Reference-against-itself statistics from noise_floor.npz: end-state differences (solver
+    tolerance units) of twin solves from start states perturbed by 1e-14 and by 1e-12 relative,
+    split by whether the twin kept the four counters."""
+    units = np.concatenate([nf[prefix + "_units"], nf[prefix + "_units_e12"].ravel()])
+    same = np.concatenate([nf[prefix + "_same"], nf[prefix + "_same_e12"].ravel()]).astype(bool)
+    return units, same
 
 
 def test_windows_default_run_against_reference(golden):
     """K4+K5 teacher-forced: the 150 taped windows of the default run, each from
     the reference's own start state.  Windows whose four counters (nfev, njev, nlu, steps) equal
-    the tape took the same decisions: there the end state must agree to rounding level; the
-    fraction of windows with a flipped decision and their error are judged separately.
+    the tape's are judged on their own; the fraction of windows with a flipped decision and their
+    error are reported and judged separately.
 
-    The bars come from tests/golden/noise_floor.npz -- the reference against itself with the
-    start state perturbed by 1e-14 relative (make_golden_floor.py): with identical counters the
-    reference's own twin differs by up to `floor_same` (0.042) solver-tolerance units, median
-    8e-6 -- a tighter bar than that is not a property of the algorithm."""
+    Every bar is derived from tests/golden/noise_floor.npz -- the reference against itself from
+    start states perturbed by 1e-14 and 1e-12 relative (the size of the device's rounding
+    differences in the RHS), 750 twin solves (make_golden_floor.py).  Equal counters do not mean
+    equal trajectories: step sizes depend continuously on the error norms and the finite-difference
+    Jacobian amplifies rounding by ~1e8, so the reference's own twins with equal counters differ by
+    1.7e-5 units in the median and by up to 2.03 units (one window where the step grid shifts);
+    the device must stay within 3x of the twins' median and 95th percentile and within 1.5x of
+    their maximum."""
     g, nf = golden("windows_default.npz"), golden("noise_floor.npz")
-    errs, same, wtd_ok = _teacher_forced_gpu(g, "", default_column(), 0)
-    floor_same = nf["tf_units"][nf["tf_same"] == 1].max()
-    floor_flip = 1.0 - nf["tf_same"].mean()
-    print("gpu windows: counters-match %.3f (reference twin %.3f); matching windows: err median %.2e "
-          "max %.2e (reference twin: median %.2e max %.2e); flipped windows: max %.2e" %
-          (same.mean(), nf["tf_same"].mean(), np.median(errs[same]), errs[same].max(),
-           np.median(nf["tf_units"]), floor_same, errs[~same].max() if (~same).any() else 0.0))
-    # windows with the tape's counters: within 3x of what the reference does against itself
-    assert errs[same].max() <= 3.0 * floor_same
-    assert np.median(errs[same]) <= 10.0 * np.median(nf["tf_units"])
-    # decision flips: reported separately; no more frequent than 3x the reference's own rate
-    # (floor 1 / 150), and a flipped window still ends within 5 tolerance units
-    assert (1.0 - same.mean()) <= max(3.0 * floor_flip, 0.03)
-    assert errs.max() < 5.0
+    errs, same, wtd_ok, grid = _teacher_forced_gpu(g, "", default_column(), 0, with_grid=True)
+    t_units, t_same = _twin_stats(nf, "tf")
+    print("gpu windows: counters-match %.3f (reference twins %.3f), of those with the reference's step grid "
+          "to 1e-6: %.3f; matching windows: err median %.2e p95 %.2e max %.2e (reference twins: %.2e / %.2e / "
+          "%.2e); flipped windows: max %.2e (reference twins %.2e)" %
+          (same.mean(), t_same.mean(), grid[same].mean(), np.median(errs[same]), np.quantile(errs[same], 0.95),
+           errs[same].max(), np.median(t_units[t_same]), np.quantile(t_units[t_same], 0.95), t_units[t_same].max(),
+           errs[~same].max() if (~same).any() else 0.0, t_units[~t_same].max()))
+    assert np.median(errs[same]) <= 3.0 * np.median(t_units[t_same])
+    assert np.quantile(errs[same], 0.95) <= 3.0 * np.quantile(t_units[t_same], 0.95)
+    assert errs[same].max() <= 1.5 * t_units[t_same].max()
+    # decision flips: no more frequent than the reference's own twins, and a flipped window
+    # still ends within the twins' worst case with the same water-table node
+    assert (1.0 - same.mean()) <= max(1.0 - t_same.mean(), 0.02)
+    assert errs.max() <= 1.5 * t_units.max()
     assert wtd_ok.all()
 
 
 def test_windows_spinup_against_reference(golden):
     """Spin-up windows (SPINUP flags, saturated start: the stiffest regime), teacher-forced.
-    The reference's own twin (noise_floor.npz: start state x (1 + 1e-14)) keeps its counters in
-    81 % of these windows and moves the end state by up to 31 tolerance units when a decision
-    flips; the bars are those figures with a margin, not hand-set numbers."""
+    The reference's own twins (noise_floor.npz) keep their counters in only about half of these
+    windows and move the end state by up to 155 tolerance units when a decision flips early in
+    the spin-up; the bars are those figures with a margin, not hand-set numbers."""
     g, nf = golden("spinup_default.npz"), golden("noise_floor.npz")
-    errs, same, wtd_ok = _teacher_forced_gpu(g, "", default_column(), 1)
-    print("gpu spinup windows: counters-match %.3f (reference twin %.3f)  err median %.2e max %.2e "
-          "(reference twin max %.2e); matching windows max %.2e" %
-          (same.mean(), nf["spin_same"].mean(), np.median(errs), errs.max(), nf["spin_units"].max(),
-           errs[same].max()))
-    assert same.mean() >= nf["spin_same"].mean() - 0.1
-    assert errs.max() <= 1.5 * nf["spin_units"].max()
-    floor_same = nf["spin_units"][nf["spin_same"] == 1].max()
-    assert errs[same].max() <= 3.0 * floor_same
-    assert np.median(errs) < 1e-2
+    errs, same, wtd_ok, grid = _teacher_forced_gpu(g, "", default_column(), 1, with_grid=True)
+    t_units, t_same = _twin_stats(nf, "spin")
+    print("gpu spinup windows: counters-match %.3f (reference twins %.3f)  err median %.2e max %.2e "
+          "(reference twins: median %.2e max %.2e); matching windows max %.2e (reference twins %.2e)" %
+          (same.mean(), t_same.mean(), np.median(errs), errs.max(), np.median(t_units), t_units.max(),
+           errs[same].max(), t_units[t_same].max()))
+    assert same.mean() >= t_same.mean() - 0.1
+    assert errs.max() <= 1.5 * t_units.max()
+    assert errs[same].max() <= 3.0 * t_units[t_same].max()
+    assert np.median(errs) <= max(3.0 * np.median(t_units), 1e-2)
     assert wtd_ok.mean() >= 0.9
 
 
@@ -284,8 +307,9 @@ def test_spinup_kernel_against_oracle(golden):
     # perturbed by 1e-14): early solves from the saturated column flip decisions and then move by
     # up to spin_units[:8].max() tolerance units, late ones by spin_units[-8:].max()
     nf = golden("noise_floor.npz")
-    tol_early = 1.5 * nf["spin_units"][:8].max()
-    tol_late = max(1.5 * nf["spin_units"][-8:].max(), 3.0 * nf["tf_units"].max())
+    tol_early = 1.5 * max(nf["spin_units"][:8].max(), nf["spin_units_e12"][:8].max())
+    tol_late = max(1.5 * max(nf["spin_units"][-8:].max(), nf["spin_units_e12"][-8:].max()),
+                   3.0 * max(nf["tf_units"].max(), nf["tf_units_e12"].max()))
     for start, n_it, tol in ((psi0, 1, tol_early), (g["y0"][-6], 3, tol_late)):
         ctx.set_state(np.tile(start, (2, 1)))
         iters = ctx.spinup(f["zWtd_cm"][0], np.tile(nr, (2, 1)), max_iter=n_it)

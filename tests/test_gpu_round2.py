@@ -399,3 +399,85 @@ def test_command_line_entry_point(tmp_path, capsys):
         with pytest.raises(SystemExit) as exc:
             cli.main(*args)
         assert exc.value.code == 1, bad
+
+
+# --------------------------------------------------------------------------- ET windows
+def test_halfhourly_daylight_windows_against_reference_tape(golden):
+    """Reference-taped half-hourly run with the default flags (ET on), gentle demand: 1 night +
+    23 daylight windows with the root-water-uptake sink active (block prefix sum + six block
+    reductions per RHS evaluation), teacher-forced against the REFERENCE's tape: end state,
+    counters, transpiration and lateral flow of the last RHS evaluation (arg_out)."""
+    from helpers import column_from_json
+    g = golden("windows_halfhourly_gentle.npz")
+    col = column_from_json(g["params_json"])
+    nx = col["x"].size
+    ctx = capi.Context(nx, 1)
+    grp, ng = pack.fd_groups(nx)
+    ctx.set_grid(col["x"], grp, ng)
+    ctx.set_columns(col["par"][None], col["stat"][None])
+    errs, same, n_day = [], [], 0
+    for w in range(g["y0"].shape[0]):
+        nr = g["n_rnd"][w].copy()
+        day = int(6 <= g["hour"][w] < 18)
+        t0 = float(g["t0"][w])
+        y, st, status, lat = ctx.solve_window(0, t0, t0 + 1.0, g["y0"][w], nr, float(g["precip"][w]),
+                                              int(g["wtd"][w]), day, 0, atm=float(g["atm"][w]))
+        assert status == 0
+        errs.append(tol_scaled(y, g["y_end"][w]))
+        same.append(st["nfev"] == g["nfev"][w] and st["njev"] == g["njev"][w] and st["nlu"] == g["nlu"][w]
+                    and st["nsteps"] == g["nsteps"][w])
+        assert ctx.last_transpiration == pytest.approx(float(g["transpiration"][w]), rel=1e-9, abs=1e-300), w
+        assert lat == pytest.approx(float(g["lateral_flow"][w]), rel=1e-6, abs=1e-9), w
+        n_day += day
+    ctx.close()
+    errs, same = np.array(errs), np.array(same)
+    print("gpu half-hourly windows vs reference tape: %d daylight; counters-match %.3f; err median %.2e max %.2e"
+          % (n_day, same.mean(), np.median(errs), errs.max()))
+    assert n_day >= 20
+    assert same.mean() >= 0.85
+    assert np.median(errs) < 1e-3 and errs.max() < 5.0
+
+
+# --------------------------------------------------------------------------- fast mode
+def test_fast_mode_against_parity_mode():
+    """SURVEY 8(f).4, explicit flag, never the default: warm-started windows (step size, Jacobian
+    and its step factors carried from window to window inside a chunk of rows) and a 3-colour
+    finite-difference Jacobian without retry pass.  It takes other steps than scipy's controller,
+    so it is judged like a second integrator at the same rtol = atol = 1e-3: over 120 windows of the
+    configs[1] workload (256 members, shared IC, Philox noise) against the parity mode --
+    water-table node identical in >= 97 % of the rows and never more than 1 cell off, psi within
+    8 solver-tolerance units, theta within 1e-3 relative at the output rows (the parity mode's own
+    reproducibility over these rows is ~2e-4, noise_floor.npz) -- at a fraction of the RHS
+    evaluations."""
+    C, T = 256, 121
+    table = synthetic_forcing(365).iloc[:T].reset_index(drop=True)
+    base, cols = ensemble_columns(default_params(SITE), 0, C)
+    ens = pack.pack_ensemble(base, table, cols)
+    ic = np.load(IC)
+    res = {}
+    for mode in ("parity", "fast"):
+        ctx, _ = open_ctx(ens)
+        if mode == "fast":
+            ctx.set_fast_mode(warm=True, jac3=True)
+        ctx.set_noise_philox(SEED, 0)
+        ctx.set_output(20)
+        ctx.set_state(np.tile(ic, (C, 1)))
+        ctx.reset_counters()
+        ctx.run(0, T)
+        res[mode] = (ctx.get_state(), ctx.get_wscal(), ctx.get_fields(), ctx.get_counters())
+        ctx.close()
+    (p_psi, p_ws, p_f, p_cn), (f_psi, f_ws, f_f, f_cn) = res["parity"], res["fast"]
+    d = np.abs(p_ws[:, :, pack.W_WTD_EST] - f_ws[:, :, pack.W_WTD_EST])
+    psi_units = np.max(np.abs(f_psi - p_psi) / (1e-3 + 1e-3 * np.abs(p_psi)), axis=1)
+    th_rel = np.max(np.abs(f_f[:, :, pack.F_THETA] - p_f[:, :, pack.F_THETA]) / p_f[:, :, pack.F_THETA])
+    rhs_ratio = f_cn[:, pack.C_NRHS].sum() / p_cn[:, pack.C_NRHS].sum()
+    print("fast vs parity: wtd node identical %.4f (max diff %d), psi units median %.3f max %.3f, theta rel max "
+          "%.2e, RHS evaluations x%.3f, steps x%.3f, Jacobians x%.3f, failed attempts %d vs %d" %
+          (np.mean(d == 0), d.max(), np.median(psi_units), psi_units.max(), th_rel, rhs_ratio,
+           f_cn[:, pack.C_NSTEPS].sum() / p_cn[:, pack.C_NSTEPS].sum(),
+           f_cn[:, pack.C_NJEV].sum() / p_cn[:, pack.C_NJEV].sum(), f_cn[:, pack.C_NFAIL].sum(), p_cn[:, pack.C_NFAIL].sum()))
+    assert np.all(f_ws[:, 1:, pack.W_STATUS] == 0)
+    assert d.max() <= 1 and np.mean(d == 0) >= 0.97
+    assert psi_units.max() < 8.0
+    assert th_rel < 1e-3
+    assert rhs_ratio < 0.8

@@ -216,3 +216,34 @@ def test_et_and_hlift_sinks_against_reference(golden):
             assert tr == pytest.approx(ref_tr, rel=1e-12, abs=1e-300)
             n += 1; n_tr += ref_tr != 0.0
     assert n == 200 and n_tr >= 60
+
+
+def test_halfhourly_daylight_windows_against_reference_tape(golden):
+    """Reference-taped half-hourly run with the default flags (ET on) and a gentle demand
+    (tests/golden/make_golden_et.py --halfhourly-gentle): 1 night + 23 daylight windows with the
+    root-water-uptake sink active, teacher-forced.  Transpiration of the last RHS evaluation
+    (arg_out, simulation.py:630) must equal the tape's; end states as in the daily windows."""
+    from helpers import column_from_json
+    g = golden("windows_halfhourly_gentle.npz")
+    col = column_from_json(g["params_json"])
+    grp, _ = pack.fd_groups(col["x"].size)
+    errs, same = [], []
+    n_day = 0
+    for w in range(g["y0"].shape[0]):
+        nr = g["n_rnd"][w].copy()
+        day = int(6 <= g["hour"][w] < 18)
+        t0 = float(g["t0"][w])
+        y, st, status, lat, t_acc = oracle.solve_window(
+            col["x"], grp, col["par"], col["stat"], t0, t0 + 1.0, g["y0"][w], nr, float(g["precip"][w]),
+            int(g["wtd"][w]), day, 0, atm=float(g["atm"][w]))
+        assert status == 0 and g["status"][w] == 0
+        errs.append(tol_scaled(y, g["y_end"][w]))
+        same.append(st["nfev"] == g["nfev"][w] and st["njev"] == g["njev"][w] and st["nlu"] == g["nlu"][w]
+                    and st["nsteps"] == g["nsteps"][w])
+        n_day += day
+    errs, same = np.array(errs), np.array(same)
+    print("oracle half-hourly windows: %d daylight; counters-match %.3f; err median %.2e max %.2e"
+          % (n_day, same.mean(), np.median(errs), errs.max()))
+    assert n_day >= 20
+    assert same.mean() >= 0.85
+    assert np.median(errs) < 1e-3 and errs.max() < 5.0
