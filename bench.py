@@ -423,7 +423,7 @@ def main():
     if a.no_adaptive:
         ctx.set_schedule(False)
     if a.fast:
-        ctx.set_fast_mode(warm=True, jac3=True)
+        ctx.set_fast_mode(cont=True, jac3=True)
         config["mode"] = "FAST (hb_set_fast_mode: warm-started windows, 3-colour FD Jacobian) -- not parity mode"
 
     def upload():

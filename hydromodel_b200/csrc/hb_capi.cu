@@ -374,7 +374,7 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     if (tuning_env("HB_NO_ADAPTIVE")) ctx->adaptive = false;
     { long long *pc; if (dev_alloc(ctx, &pc, 16)) { hb_destroy(ctx); return nullptr; } d.phase_cycles = pc; }
     if (const char *v = tuning_env("HB_CHUNK")) { const int w = atoi(v); if (w > 0) d.chunk = w; }
-    d.dbg = 0;
+    d.dbg = 0; d.fast = 0;
 #if HB_DUP_PROBE
     if (const char *v = tuning_env("HB_DBG")) d.dbg = atoi(v);
 #endif
@@ -694,7 +694,9 @@ int hb_run(hb_ctx *ctx, int w0, int w1)
         CK(cudaMemsetAsync(d.cost, 0, (size_t)d.n_cols * sizeof(long long), ctx->stream));
     }
     if (ctx->fast_flags) {
-        // fast mode (never the default): warm-started windows, 3-colour Jacobian without retry pass
+        // fast mode (never the default): continuation across windows with unchanged forcing,
+        // 3-colour Jacobian without retry pass
+        k.fast = ctx->fast_flags;
         if (ctx->fast_flags & HB_FAST_JAC3) { k.grp = ctx->grp3; k.ng = 3; }
         DISPATCH_RUN(ctx, true, grid, k, w0, w1);
     } else {
@@ -770,7 +772,7 @@ int hb_reset_counters(hb_ctx *ctx)
 int hb_set_fast_mode(hb_ctx *ctx, int flags)
 {
     if (!ctx) return fail("null ctx");
-    if (flags & ~(HB_FAST_WARM | HB_FAST_JAC3)) return fail("hb_set_fast_mode: unknown flag");
+    if (flags & ~(HB_FAST_CONT | HB_FAST_JAC3)) return fail("hb_set_fast_mode: unknown flag");
     ctx->fast_flags = flags;
     return 0;
 }

@@ -67,6 +67,7 @@ struct DevCtx {
     double *t_acc;           // test hook only: accepted step times of the current solve ([nx]), else null
     int *err_flags;          // [1] HB_ERR_* bits raised by kernels, checked by hb_sync / hb_get_*
     int chunk;               // windows per work item of run_kernel
+    int fast;                // HB_FAST_* flags of the fast build of run_kernel (0 in parity mode)
     int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice
     double sqrt_nx;          // sqrt((double)nx), the denominator of the RMS norm
     double newton_tol;       // max(10 eps / rtol, min(0.03, sqrt(rtol)))  (bdf.py:220)

@@ -955,9 +955,13 @@ __device__ __forceinline__ void column_stats(const double *fb, const double *fn,
 // Fast mode only (never the default): what one window hands to the next
 // one of the same column inside a chunk of rows.
 struct Warm {
-    double h;        // step size the controller proposed after the last accepted step (0: none)
-    bool have_J;     // V_JL/V_JD/V_JU hold a Jacobian of this column (possibly of an earlier window)
-    bool have_fac;   // the finite-difference step factors of this column are in the scratch row
+    double h;        // step size the controller proposed after the last accepted step
+    int order, n_equal;
+    bool valid;      // the previous window of this column ended successfully in this CTA: difference
+                     // table (scratch rows), Jacobian rows and step factors are those of its last step
+    bool cont;       // set by the caller: the right-hand side of this window is the same function as in
+                     // the previous one (same forcing row values, same noise field) -> continue the
+                     // multistep integration instead of restarting it
 };
 
 template <int NT, int CPT, bool FULL, bool FAST = false>
@@ -991,9 +995,26 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
 
     __syncthreads();
     // __ldcg: the state may have been written by another SM (time-sliced columns)
-    for (int i = tid; i < nx; i += NT) { const double v = __ldcg(y_glob + i); y[i] = v; D[i] = v; }
+    if (!(FAST && warm->valid && warm->cont))
+        for (int i = tid; i < nx; i += NT) { const double v = __ldcg(y_glob + i); y[i] = v; D[i] = v; }
+
+    // Fast mode, continuation: the previous window of this column ended at t0 with the same
+    // right-hand-side function; the BDF history (order, step size, difference table) and the
+    // Jacobian are still those of its last step, so the integration simply goes on to the new
+    // t_bound -- no select_initial_step, no new Jacobian, no restart at order 1 (what scipy does
+    // at every solve_ivp call, bdf.py:198-241, ivp.py:582-660).
+    bool resume = false;
+    if (FAST) {
+        resume = warm->valid && warm->cont;
+        if (resume) { order = warm->order; n_equal = warm->n_equal; h_abs = warm->h; t = wa[WA_T0]; }
+        warm->valid = false;
+    }
 
     for (;;) {
+        int go = GO_NONE;
+        bool jb_now = false;
+        if (FAST && resume) { resume = false; go = GO_STEP_BEGIN; }
+        else {
         // ======== the single right-hand-side evaluation ========================
         const int out = (state == S_JB) ? V_TW : (state == S_JG || state == S_JR) ? V_TIP : V_B;
         __syncthreads();
@@ -1004,8 +1025,6 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         rhs_eval<NT, CPT, NV>(c, S, col, out, par_);
         HB_TICK(c, NV, 2);                   // assembly phase
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
-        int go = GO_NONE;
-        bool jb_now = false;
 
         if (state == S_NW) {
             // ---- one Newton iteration (solve_bdf_system, bdf.py:41-67) --------
@@ -1171,22 +1190,6 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     go = GO_STEP_BEGIN;
                 }
             }
-        } else if (FAST && state == S_F0 && warm->h > 0.0) {
-            // ---- fast mode, warm start: no select_initial_step; the first step is the one
-            // the controller proposed at the end of the previous window of this column, and
-            // the Jacobian of that window is kept until a Newton iteration fails to converge
-            // (bdf.py:375-380 then refreshes it).  Order restarts at 1 as in a new solver.
-            h_abs = fmin(warm->h, fabs(wa[WA_TBOUND] - wa[WA_T0]));
-            if (warm->have_J) {
-                for (int i = tid; i < nx; i += NT) D[nxp + i] = b[i] * h_abs;         // D[1] = f0 * h
-                order = 1; n_equal = 0; t = wa[WA_T0];
-                lu_valid = false;
-                go = GO_STEP_BEGIN;
-            } else {
-                for (int i = tid; i < nx; i += NT) { const double f0 = b[i]; D[nxp + i] = f0; ybv[i] = D[i]; fbv[i] = f0; }
-                jac_first = !warm->have_fac; jac_init = true;
-                jb_now = true;
-            }
         } else if (state == S_F0) {
             // ---- select_initial_step, first half (common.py:105-115) ----------
             double l0 = 0.0, l1 = 0.0;
@@ -1277,6 +1280,8 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
             }
         }
 
+        }   // (not resuming)
+
         if (jb_now) {
             // ---- num_jac: steps from the base value (common.py:320-341) -------
             HB_FOR_CELLS(i) {
@@ -1328,7 +1333,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         if (go == GO_STEP_BEGIN) {
             // ---- driver loop / top of _step_impl (ivp.py:659, bdf.py:318-333) --
             if (t == wa[WA_TBOUND]) {
-                if (FAST) { warm->h = h_abs; warm->have_J = true; warm->have_fac = true; }
+                if (FAST) { warm->h = h_abs; warm->order = order; warm->n_equal = n_equal; warm->valid = true; }
                 __syncthreads();
                 return 0;
             }
@@ -1348,7 +1353,6 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                 __syncthreads();
                 for (int i = tid; i < nx; i += NT) y[i] = D[i];
                 __syncthreads();
-                if (FAST) { warm->h = 0.0; warm->have_J = false; }
                 return -1;
             }
             t_new = t + h_loc;

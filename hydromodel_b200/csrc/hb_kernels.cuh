@@ -119,14 +119,16 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
             for (int i = tid; i < nx; i += NT) { nr[i] = __ldcg(nb + i); y[i] = __ldcg(psi_g + i); }
             bool nr_is_base = true;
             long long windows = 0;
-            Warm warm = {0.0, false, false};       // fast mode: nothing is carried into a chunk
+            Warm warm = {0.0, 1, 0, false, false};  // fast mode: nothing is carried into a chunk
+            double prev_p = 0.0, prev_atm = 0.0;
+            int prev_wtd = -2, prev_mode = -1;
             __syncthreads();
             for (int row = r0; row < r1; ++row) {
                 int status = 0;
                 bool solved = false;
                 if (row > 0) {
                     const int wtd = c.wtd_idx[(size_t)ser * c.T + row];
-                    if (wtd < 0) status = 2;
+                    if (wtd < 0) { status = 2; if (FAST) warm.valid = false; }
                     else {
                         const double p = HB_XA(c, NV, X_PAR)[HB_P_PRECIP_MULT] * c.precip[(size_t)ser * c.T + row];
                         const bool refresh = (p > 0.5) || (row % 48 == 0);   // simulation.py:599
@@ -154,8 +156,16 @@ __global__ void __launch_bounds__(NT, MB) run_kernel(const __grid_constant__ Dev
                         a.mode = c.daylight[(size_t)ser * c.T + row] ? 1 : 0;
                         a.atm = c.atm ? c.atm[(size_t)ser * c.T + row] : 0.0;
                         bool damped = false;
+                        if (FAST) {
+                            // same function of (t, psi) as in the previous window: same row values and the
+                            // same noise field (both windows on the base field, no refresh in between)
+                            warm.cont = !refresh && nr_is_base && p == prev_p && wtd == prev_wtd &&
+                                        a.mode == prev_mode && a.atm == prev_atm && (c.fast & HB_FAST_CONT);
+                            prev_p = refresh ? -1.0 : p; prev_wtd = wtd; prev_mode = a.mode; prev_atm = a.atm;
+                        }
                         status = solve_window<NT, CPT, FULL, FAST>(c, col, a, (double)(row - 1), (double)row, psi_g,
                                                                    damped, &warm);
+                        if (FAST && (status != 0 || damped)) warm.valid = false;
                         if (damped && nr_is_base)
                             for (int i = tid; i < nx; i += NT) __stcg(nb + i, nr[i]);
                         for (int i = tid; i < nx; i += NT) __stcg(psi_g + i, y[i]);

@@ -258,6 +258,11 @@ class EnsembleSimulation:
         else:
             ctx.set_noise_philox(self.seed, self.first_column)
         ctx.set_output(out_stride)
+        if out_stride > 0:
+            # the result file: fail before the run, not after it, if the built-in writer could not hold it
+            from .src import hdf5_io, hdf5_min
+            if hdf5_io._h5py() is None:
+                hdf5_min.check_writable([(n, ctx.n_output_rows, nx)])
         ctx.set_state(m["initial_cond"])
         ctx.reset_counters()
         ctx.run(0, T)

@@ -87,6 +87,21 @@ def _normalise(arr):
     return np.require(arr.astype(arr.dtype.newbyteorder("<"), copy=False), requirements="C")
 
 
+def check_writable(shapes, itemsize=8):
+    """Raise HDF5FormatError now if a dataset of one of ``shapes`` could not be stored by
+    ``write_file`` (each dataset is cut into at most 64 chunks along its first axis and a chunk
+    must stay below 4 GiB) -- so that a long run learns it before it starts, not at save time."""
+    for shape in shapes:
+        shape = tuple(int(d) for d in shape)
+        if not shape or 0 in shape:
+            continue
+        rows = -(-shape[0] // (2 * CHUNK_BTREE_K))
+        cbytes = rows * int(np.prod(shape[1:], dtype=np.int64)) * itemsize
+        if any(d >= 2 ** 32 for d in shape) or cbytes >= 2 ** 32:
+            raise HDF5FormatError(f"a dataset of shape {shape} is too large for the built-in HDF5 writer "
+                                  f"(64 chunks of < 4 GiB); decimate the output (out_stride) or install h5py")
+
+
 def write_file(path, datasets, compression_level=4, chunk_rows=None):
     """Write ``{name: ndarray}`` as root-level datasets (gzip level 4 = h5py's default
     for ``compression='gzip'``).  ``compression_level=None`` stores contiguous raw data.
@@ -224,9 +239,15 @@ def write_file(path, datasets, compression_level=4, chunk_rows=None):
 # =============================================================================== reader
 class _Reader:
     def __init__(self, buf):
-        self.b = buf
-        if buf[:8] != SIGNATURE:
-            raise HDF5FormatError("not an HDF5 file (signature)")
+        # the superblock sits at byte 0 or, behind a user block, at 512, 1024, 2048, ... (spec
+        # III.A); every address in the file is relative to the superblock's base address
+        sb = 0
+        while buf[sb:sb + 8] != SIGNATURE:
+            sb = 512 if sb == 0 else 2 * sb
+            if sb + 8 > len(buf):
+                raise HDF5FormatError("not an HDF5 file (signature)")
+        whole = buf
+        buf = buf[sb:]
         ver = buf[8]
         if ver not in (0, 1):
             raise HDF5FormatError(f"superblock version {ver} is not supported (0 and 1 are)")
@@ -236,8 +257,12 @@ class _Reader:
         self.base, _, self.eof, _ = struct.unpack_from("<QQQQ", buf, off)
         off += 32
         _, self.root_oh, cache, _ = struct.unpack_from("<QQII", buf, off)
-        if self.eof > len(buf) + self.base:
+        if self.base not in (0, sb):
+            raise HDF5FormatError("base address differs from the superblock's position")
+        if self.eof > len(whole):
             raise HDF5FormatError("file is truncated (end-of-file address beyond the file)")
+        self.b = buf                                   # addresses below are offsets into this view
+        self.base = 0
 
     # ---- object headers
     def messages(self, addr):
@@ -308,9 +333,22 @@ class _Reader:
                 layout = d
         if shape is None or dtype is None or layout is None:
             raise HDF5FormatError("dataset without dataspace / datatype / layout")
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        if layout[0] in (1, 2):
+            # versions 1 and 2 (libhdf5 <= 1.6): dimensionality, class, 5 reserved bytes, the
+            # address (absent for compact data), 4-byte dimensions, then the element size
+            # (chunked) or the compact data; rewritten here in the version-3 form used below
+            nd, cls = layout[1], layout[2]
+            if cls == 0:
+                size, = struct.unpack_from("<I", layout, 8 + 4 * nd)
+                layout = bytes([3, 0]) + struct.pack("<H", size) + layout[12 + 4 * nd:12 + 4 * nd + size]
+            elif cls == 1:
+                addr, = struct.unpack_from("<Q", layout, 8)
+                layout = bytes([3, 1]) + struct.pack("<QQ", addr, n * dtype.itemsize)
+            elif cls == 2:
+                layout = bytes([3, 2, nd]) + layout[8:16] + layout[16:16 + 4 * nd]
         if layout[0] != 3:
             raise HDF5FormatError(f"data layout message version {layout[0]} is not supported")
-        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
         cls = layout[1]
         if cls == 0:                                       # compact
             size, = struct.unpack_from("<H", layout, 2)

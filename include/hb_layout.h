@@ -104,11 +104,13 @@ enum {                       /* output field ids for hb_get_field           */
 /* Fast mode (hb_set_fast_mode; never the default -- results then differ from the
  * reference's arithmetic within the integrator's own tolerance).
  * Either flag selects the fast build of the window loop. */
-#define HB_FAST_WARM     1   /* windows of a column inside a chunk of rows are warm-started:
-                              * first step = the step size proposed at the end of the previous
-                              * window (no select_initial_step, scipy common.py:63-134), Jacobian
-                              * and its step factors carried over until Newton fails to converge
-                              * (scipy builds a new Jacobian at every solve_ivp call, bdf.py:198-241) */
+#define HB_FAST_CONT     1   /* a window whose forcing row (precipitation, water-table observation,
+                              * day/night, demand) and noise field equal the previous window's is
+                              * integrated as the CONTINUATION of that window: order, step size,
+                              * difference table and Jacobian carry on and the steps are clipped at
+                              * the window ends only.  scipy restarts at every solve_ivp call
+                              * (select_initial_step common.py:63-134, order 1 and a new Jacobian
+                              * bdf.py:198-241); windows with new forcing still restart that way */
 #define HB_FAST_JAC3     2   /* finite-difference Jacobian with the 3 colours j mod 3 instead of
                               * scipy's 5 groups, and without the 10x-step retry pass
                               * (common.py:268-455, _numdiff.py:227-284) */

@@ -17,8 +17,9 @@ Recorded (reference @ container stack, see make_golden.py):
             difference in solver-tolerance units, theta relative difference,
             whether the four counters agree (`same`), whether in addition the
             accepted time grids coincide (`grid`: same decisions), water-table node
-            difference; `*_e12`: the same for four random perturbation patterns of
-            size 1e-12 (the size of the device's rounding differences in the RHS).
+            difference; `*_e12`: the same for four twins that model an independent
+            implementation: start state AND every RHS evaluation perturbed by random
+            patterns of relative size 1e-12 (the RHS parity bar of device and oracle).
   spin_*    the same for the first 24 and last 8 solves of the spin-up
             (simulation.py:444-480) -- the saturated start is the stiffest regime.
   free_*    free-running twins: two reference runs of 150 windows from IC and
@@ -64,8 +65,16 @@ def _twin_solve_ivp(fun, t_span, y0, **kw):
     oracle's rounding differences in the right-hand side (1e-12 relative, RHS parity test)."""
     y0 = np.asarray(y0, dtype=float)
     twin = _real(fun, t_span=t_span, y0=y0 * (1.0 + EPS), **kw)
-    twins12 = [_real(fun, t_span=t_span, y0=y0 * (1.0 + 1e-12 * _RNG.standard_normal(y0.size)), **kw)
-               for _ in range(N_E12)]
+    # an independent implementation differs in the rounding of every RHS evaluation, not only in
+    # the start state: the 1e-12 twins also multiply dpsi/dt by (1 + 1e-12 * pattern), a fixed
+    # random pattern per twin (the RHS parity bar of the device and of the oracle is 1e-12)
+    twins12 = []
+    for _ in range(N_E12):
+        pat_y, pat_f = _RNG.standard_normal(y0.size), _RNG.standard_normal(y0.size)
+
+        def fun_pert(t, y, *a, _p=pat_f):
+            return np.asarray(fun(t, y, *a)) * (1.0 + 1e-12 * _p)
+        twins12.append(_real(fun_pert, t_span=t_span, y0=y0 * (1.0 + 1e-12 * pat_y), **kw))
     sol = _real(fun, t_span=t_span, y0=y0, **kw)
     c14, g14 = _same(twin, sol)
     rec = {"units": _units(twin.y[:, -1], sol.y[:, -1]), "same": c14, "grid": g14,

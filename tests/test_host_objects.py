@@ -4,6 +4,8 @@ the reference's own unit tests (code/tests/test_*.py: range validation, profile
 bounds, root-pdf normalisation, closure shapes / round trip) and add checks
 against the golden outputs of the reference's closures.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -268,3 +270,48 @@ def test_save_and_load_results_like_the_reference(tmp_path):
     assert path.endswith("Sim_00.h5")
     back = load_datasets(path)
     assert all(np.array_equal(back[k], np.asarray(v)) for k, v in data.items())
+
+
+def test_hdf5_reader_on_a_file_written_by_libhdf5():
+    """The only file written by the real HDF5 library in this image: a MATLAB 7.3 file of scipy's
+    test data (512-byte user block, superblock 0, symbol-table root group, version-1 object
+    headers, version-1/2 data layout) holding testdouble = pi/4 * arange(9).  The reader walks
+    the same structures the writer emits, so this pins the format against libhdf5 itself."""
+    import scipy.io
+    from hydromodel_b200.src import hdf5_min
+    path = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(path):
+        pytest.skip("scipy's HDF5 test file is not installed")
+    data = hdf5_min.read_file(path)
+    assert list(data) == ["testdouble"]
+    assert data["testdouble"].dtype == np.float64 and data["testdouble"].shape == (9, 1)
+    assert np.array_equal(data["testdouble"].ravel(), np.pi / 4 * np.arange(9.0))
+
+
+def test_hdf5_against_h5py_when_available(tmp_path):
+    """round trips through h5py in both directions -- skipped where h5py is absent
+    (this image); runs wherever the reference's own dependency is installed."""
+    h5py = pytest.importorskip("h5py")
+    from hydromodel_b200.src import hdf5_min
+    data = {k: np.asarray(v) for k, v in _h5_sample().items() if k not in ("flag", "scalar")}
+    ours = str(tmp_path / "ours.h5")
+    hdf5_min.write_file(ours, data)
+    with h5py.File(ours, "r") as fh:                       # libhdf5 reads what we write
+        assert sorted(fh) == sorted(data)
+        for k, v in data.items():
+            assert fh[k].shape == v.shape and fh[k].dtype == v.dtype and np.array_equal(fh[k][...], v), k
+            if v.size:
+                assert fh[k].compression == "gzip"
+    theirs = str(tmp_path / "theirs.h5")
+    with h5py.File(theirs, "w") as fh:                     # we read what the reference writes
+        for k, v in data.items():
+            fh.create_dataset(k, data=v, shape=v.shape, compression="gzip")
+    back = hdf5_min.read_file(theirs)
+    assert all(np.array_equal(back[k], v) for k, v in data.items())
+
+
+def test_hdf5_size_check_before_a_run():
+    from hydromodel_b200.src import hdf5_min
+    hdf5_min.check_writable([(65536, 11, 401), (0, 5), ()])
+    with pytest.raises(hdf5_min.HDF5FormatError):
+        hdf5_min.check_writable([(65536, 3650, 401)])      # 767 GB: beyond 64 chunks of < 4 GiB
