@@ -990,6 +990,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     // controller state (identical in every thread)
     int state = S_F0, order = 1, n_equal = 0, k_newton = 0, jac_g = 0;
     bool lu_valid = false, current_jac = false, have_old = false, jac_first = true, jac_init = true;
+    bool any_accept = false;                        // a step of THIS attempt has been accepted
     double t = wa[WA_T0], t_new = t, h_abs = 0.0, h_loc = 0.0, min_step = 0.0, cc = 0.0, c_lu = 0.0;
     double dy_norm_old = 0.0, d1_init = 0.0, h0_init = 0.0;
 
@@ -1136,6 +1137,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     n_equal++;
                     t = t_new;
                     h_abs = h_loc;
+                    any_accept = true;
                     if (tid == 0) {
                         if (c.t_acc && cnt[K_NSTEPS] < nx) c.t_acc[cnt[K_NSTEPS]] = t_new;     // hb_solve_window hook
                         cnt[K_NSTEPS]++;
@@ -1349,9 +1351,13 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         if (go == GO_STEP_RETRY) {
             // ---- top of the `while not step_accepted` loop (bdf.py:345-358) ---
             if (h_loc < min_step) {
-                // failure: solver.y is the last accepted state == D[0]
+                // failure: solver.y is the last accepted state (ivp.py:659-666).  After an accepted
+                // step that is D[0]; before the first one it is the attempt's y0 -- D[0] may have
+                // been destroyed by then (a right-hand side that is not finite at t0 gives h = 0 in
+                // select_initial_step and change_D(min_step / 0) fills the table with NaN)
                 __syncthreads();
-                for (int i = tid; i < nx; i += NT) y[i] = D[i];
+                if (any_accept) { for (int i = tid; i < nx; i += NT) y[i] = D[i]; }
+                else { for (int i = tid; i < nx; i += NT) y[i] = __ldcg(y_glob + i); }
                 __syncthreads();
                 return -1;
             }

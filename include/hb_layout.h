@@ -104,8 +104,8 @@ enum {                       /* output field ids for hb_get_field           */
 /* Fast mode (hb_set_fast_mode; never the default -- results then differ from the
  * reference's arithmetic within the integrator's own tolerance).
  * Either flag selects the fast build of the window loop. */
-#define HB_FAST_CONT     1   /* a window whose forcing row (precipitation, water-table observation,
-                              * day/night, demand) and noise field equal the previous window's is
+#define HB_FAST_CONT     1   /* a window whose forcing row (precipitation, day/night, demand -- the
+                              * water-table observation may differ) and noise field equal the previous window's is
                               * integrated as the CONTINUATION of that window: order, step size,
                               * difference table and Jacobian carry on and the steps are clipped at
                               * the window ends only.  scipy restarts at every solve_ivp call
