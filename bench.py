@@ -11,9 +11,9 @@ forcing rows), whole job over all GPUs.
       synthetic daily forcing (10 years), nx = 401, vrettas_fung + Stratified, on-device Philox
       noise, shared spun-up initial state.  STRONG scaling: the 65,536 columns are split over the
       GPUs (contiguous blocks of global member ids).  One step = the window loop of Simulation.run
-      over the next `--rows-per-step` (48) forcing rows of EVERY column of the job, state carried
+      over the next `--rows-per-step` (120) forcing rows of EVERY column of the job, state carried
       from step to step (warm-up steps integrate the first rows, the timed steps the following
-      ones), so `--steps 20 --warmup 5` integrates rows 0 .. 1,200 of the 10-year table.
+      ones), so `--steps 20 --warmup 5` integrates rows 0 .. 3,000 of the 10-year table.
   --config 1 (BASELINE.json configs[1])
       1,024 columns PER GPU (weak scaling) perturbing n / a0 / psi_sat, 365-row forcing, host noise
       tape in the reference's RNG order; one step = the whole year, restarted every step.
@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--columns", type=int, default=None,
                     help="config 2: columns of the WHOLE job (65,536); config 1: columns per GPU (1,024)")
     ap.add_argument("--rows", type=int, default=None, help="forcing rows (config 2: 3,650; config 1: 365)")
-    ap.add_argument("--rows-per-step", type=int, default=48, help="config 2: forcing rows integrated per step")
+    ap.add_argument("--rows-per-step", type=int, default=120, help="config 2: forcing rows integrated per step")
     ap.add_argument("--out-stride", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spinup", action="store_true", help="skip the separately timed batched spin-up")
@@ -546,6 +546,10 @@ def main():
                 walls.append(w); fields_rows.append(nf)
         windows_per_step = n_cols * (n_rows - 1)
 
+    top = np.argsort(counters[:, pack.C_NRHS])[::-1][:5]
+    log(f"[bench] rank {rank}: costliest columns over the timed steps (global id, RHS evaluations, failed attempts): "
+        f"{[(int(first_col + c), int(counters[c, pack.C_NRHS]), int(counters[c, pack.C_NFAIL])) for c in top]}; "
+        f"median RHS evaluations per column {int(np.median(counters[:, pack.C_NRHS]))}")
     kernel_s = float(np.sum(kernel_ms)) * 1e-3
     e2e_s = float(np.sum(walls))
     log(f"[bench] rank {rank}: kernel ms per step {['%.1f' % v for v in kernel_ms]}, "
@@ -583,7 +587,9 @@ def main():
     theta_mean_ic = float(th[0, 0].mean().item()) / (total_cols if cfg2 else n_cols * n_gpus)
 
     # ---- roofline ------------------------------------------------------------------
-    flops = algorithmic_flops(counters, nx) / a.steps          # per launch (one launch per step)
+    # counters: config 2 accumulates them over the timed steps, config 1 resets them every step
+    counted_steps = a.steps if cfg2 else 1
+    flops = algorithmic_flops(counters, nx) / counted_steps    # per launch (one launch per step)
     slots = 0 if tape is None else tape.shape[1]
     abytes = algorithmic_bytes(n_cols, rps, nx, float(np.mean(fields_rows)) if cfg2 else n_out, slots)
     peaks = {}
@@ -604,7 +610,7 @@ def main():
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
         "windows_per_s": job_windows / kernel_s,
-        "rhs_evals_per_s": n_gpus * csum[pack.C_NRHS] / (float(np.sum(kernel_ms)) * 1e-3),
+        "rhs_evals_per_s": n_gpus * csum[pack.C_NRHS] / counted_steps / own_launch_s,
         "per_window": {"nfev": csum[pack.C_NFEV] / nwin, "njev": csum[pack.C_NJEV] / nwin,
                        "nlu": csum[pack.C_NLU] / nwin, "steps": csum[pack.C_NSTEPS] / nwin,
                        "rhs": csum[pack.C_NRHS] / nwin, "failed_attempts": csum[pack.C_NFAIL]},
@@ -614,6 +620,7 @@ def main():
                         "forcing, state up; per-row scalars, output fields, state down"},
         "gpu_launches": int(launches),
         "per_rank_kernel_ms_per_step": [1e3 * v / a.steps for v in per_rank_kernel_s],
+        "slowest_step_ms_this_rank": float(np.max(kernel_ms)), "median_step_ms_this_rank": float(np.median(kernel_ms)),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_fp64, "unit": "TFLOP/s",
                      "frac": ach_tf / peak_fp64, "traffic": tr["bytes"] if tr else None,
