@@ -186,6 +186,7 @@ struct hb_ctx {
     bool fixed = false;     // the compile-time nxp = 416 instance (namespace hbf) applies
     size_t smem_bytes = 0;
     int blocks_per_sm = 1;
+    bool chunk_fixed = false;  // HB_CHUNK given: no automatic chunk length
     int wscal_T = 0;        // table length the per-row result buffer was laid out for
     bool adaptive = true;   // run_kernel launch plan from the previous launch's per-column cost
     bool have_cost = false; // a previous hb_run left per-column costs on the device
@@ -269,12 +270,18 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
 //   3: <512,3,1,false>  nx <= 1536
 // STMT sees NT_, CPT_, MB_, FL_ and the instance namespace alias K (hbf: nxp fixed at 416
 // at compile time, variant 0 only; hbr: nxp at run time).
+// (HB_V0_*: shape of variant 0 in A/B builds, tools/build_alt.py; the shipped library uses 256 / 2 / 2)
+#ifndef HB_V0_NT
+#define HB_V0_NT 256
+#define HB_V0_CPT 2
+#define HB_V0_MB 2
+#endif
 #define HB_FOR_VARIANT(ctx, STMT)                                   \
     do {                                                            \
-        if ((ctx)->fixed) { namespace K = hbf; constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; constexpr bool FL_ = true; STMT; break; } \
+        if ((ctx)->fixed) { namespace K = hbf; constexpr int NT_ = HB_V0_NT, CPT_ = HB_V0_CPT, MB_ = HB_V0_MB; constexpr bool FL_ = true; STMT; break; } \
         namespace K = hbr;                                          \
         switch ((ctx)->variant) {                                   \
-        case 0: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; constexpr bool FL_ = true; STMT; } break;  \
+        case 0: { constexpr int NT_ = HB_V0_NT, CPT_ = HB_V0_CPT, MB_ = HB_V0_MB; constexpr bool FL_ = true; STMT; } break;  \
         case 1: { constexpr int NT_ = 256, CPT_ = 2, MB_ = 2; constexpr bool FL_ = false; STMT; } break; \
         case 2: { constexpr int NT_ = 512, CPT_ = 2, MB_ = 1; constexpr bool FL_ = false; STMT; } break; \
         default: { constexpr int NT_ = 512, CPT_ = 3, MB_ = 1; constexpr bool FL_ = false; STMT; } break; \
@@ -373,7 +380,7 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     }
     if (tuning_env("HB_NO_ADAPTIVE")) ctx->adaptive = false;
     { long long *pc; if (dev_alloc(ctx, &pc, 16)) { hb_destroy(ctx); return nullptr; } d.phase_cycles = pc; }
-    if (const char *v = tuning_env("HB_CHUNK")) { const int w = atoi(v); if (w > 0) d.chunk = w; }
+    if (const char *v = tuning_env("HB_CHUNK")) { const int w = atoi(v); if (w > 0) { d.chunk = w; ctx->chunk_fixed = true; } }
     d.dbg = 0; d.fast = 0;
 #if HB_DUP_PROBE
     if (const char *v = tuning_env("HB_DBG")) d.dbg = atoi(v);
@@ -685,6 +692,19 @@ int hb_run(hb_ctx *ctx, int w0, int w1)
     CK(cudaMemsetAsync(d.credit, 0, (size_t)d.n_cols * sizeof(int), ctx->stream));
     const int grid = persistent_grid(ctx);
     DevCtx k = d;
+    if (!ctx->chunk_fixed) {
+        // Rows per work item.  Every chunk re-stages the column (state, noise field, statics:
+        // ~22 KB of HBM traffic at nx = 401), so chunks should be long; the tail of the launch is
+        // one chunk, so they should be short.  Keep the tail below ~1 % of the launch:
+        // chunk <= 0.01 * (columns per resident CTA) * rows, at least 16 rows
+        // (65,536 columns x 120 rows: the whole slice in one piece, DRAM traffic of the launch
+        // 11.9 GB -> measured in profiles/; 8,192 columns: 33 rows; 1,024 columns x 365 rows: 16).
+        const long long rows = w1 - w0;
+        long long len = (long long)(0.01 * (double)d.n_cols / (double)grid * (double)rows);
+        if (len < 16) len = 16;
+        if (len > rows) len = rows;
+        k.chunk = (int)len;
+    }
     if (ctx->adaptive && ctx->have_cost && d.n_cols > grid) {
         // columns the previous launch found expensive start first and run unpaced
         plan_kernel<<<1, 1024, 0, ctx->stream>>>(d, grid / 2);
