@@ -64,6 +64,12 @@ def log(*a):
 NCU_TRAFFIC = {
     (1, 1024, 365, 30): {"bytes": 352691712 + 269521152,
                          "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"},
+    # round 2, automatic chunk length (65,536 columns: one 120-row chunk per column and launch;
+    # with round 1's fixed 16-row chunks the same launch moved 9.27 + 2.66 GB, profiles/launches_r02.csv)
+    (2, 65536, 120, 365): {"bytes": 1690220544 + 1282057472,
+                           "source": "profiles/traffic_r02_cfg2_65536.csv"},
+    (2, 8192, 120, 365): {"bytes": 617554432 + 201320448,
+                          "source": "profiles/traffic_r02_cfg2_8192.csv"},
 }
 
 
