@@ -183,6 +183,7 @@ struct hb_ctx {
     std::vector<int> h_flags;            // Simulation_Flags bitmask per column (host copy)
     std::vector<int> h_daylight, h_series;  // forcing daylight flags / series map (host copies)
     int variant = 0;        // kernel variant, see HB_FOR_VARIANT
+    int shape = 0;          // experimental shape of the fixed-length instance (HB_SHAPE), 0 = shipped
     bool fixed = false;     // the compile-time nxp = 416 instance (namespace hbf) applies
     size_t smem_bytes = 0;
     int blocks_per_sm = 1;
@@ -230,10 +231,10 @@ static const char *tuning_env(const char *name)
 {
     const char *v = getenv(name);
     if (v && *v) {
-        static bool told[8] = {false};
-        static const char *names[8] = {"HB_CARVEOUT", "HB_VARIANT", "HB_NO_FIXED", "HB_NO_TRI13", "HB_CHUNK",
-                                       "HB_DBG", "HB_NO_ADAPTIVE", "HB_TRI_DEBUG"};
-        for (int k = 0; k < 8; ++k)
+        static bool told[10] = {false};
+        static const char *names[10] = {"HB_CARVEOUT", "HB_VARIANT", "HB_NO_FIXED", "HB_NO_TRI13", "HB_CHUNK",
+                                        "HB_DBG", "HB_NO_ADAPTIVE", "HB_TRI_DEBUG", "HB_SHAPE", "HB_JAC_SEQ"};
+        for (int k = 0; k < 10; ++k)
             if (!strcmp(names[k], name) && !told[k]) {
                 told[k] = true;
                 fprintf(stderr, "[libhydrob200] tuning knob %s=%s is active\n", name, v);
@@ -271,14 +272,52 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
 // STMT sees NT_, CPT_, MB_, FL_ and the instance namespace alias K (hbf: nxp fixed at 416
 // at compile time, variant 0 only; hbr: nxp at run time).
 // (HB_V0_*: shape of variant 0 in A/B builds, tools/build_alt.py; the shipped library uses 256 / 2 / 2)
+#ifndef HB_SHAPES
+#define HB_SHAPES 0
+#endif
 #ifndef HB_V0_NT
 #define HB_V0_NT 256
 #define HB_V0_CPT 2
 #define HB_V0_MB 2
 #endif
+#ifndef HB_V0_FULL
+#define HB_V0_FULL true
+#endif
+// -DHB_LEAN=1 (A/B builds only): compile the fixed-length instance alone (401-node grids, parity mode)
+#ifndef HB_LEAN
+#define HB_LEAN 0
+#endif
+// Experimental shapes of the fixed-length instance (HB_SHAPE=n, A/B builds with -DHB_SHAPES=1):
+//   1: <32,13,4,false>  one warp per column, 4 columns per SM
+//   2: <64,7,4,false>   two warps per column
+//   3: <128,4,4,false>  four warps per column, 4 columns per SM
+//   4: <32,13,3,true>   one warp per column, statics in shared memory, 3 columns per SM
+#if HB_SHAPES
+#define HB_EXTRA_SHAPES(STMT) \
+            case 1: { constexpr int NT_ = 32, CPT_ = 13, MB_ = 4; constexpr bool FL_ = false; STMT; } break; \
+            case 2: { constexpr int NT_ = 64, CPT_ = 7, MB_ = 4; constexpr bool FL_ = false; STMT; } break; \
+            case 3: { constexpr int NT_ = 128, CPT_ = 4, MB_ = 4; constexpr bool FL_ = false; STMT; } break; \
+            case 4: { constexpr int NT_ = 32, CPT_ = 13, MB_ = 3; constexpr bool FL_ = true; STMT; } break;
+#else
+#define HB_EXTRA_SHAPES(STMT)
+#endif
 #define HB_FOR_VARIANT(ctx, STMT)                                   \
     do {                                                            \
-        if ((ctx)->fixed) { namespace K = hbf; constexpr int NT_ = HB_V0_NT, CPT_ = HB_V0_CPT, MB_ = HB_V0_MB; constexpr bool FL_ = true; STMT; break; } \
+        if ((ctx)->fixed) {                                         \
+            namespace K = hbf;                                      \
+            switch ((ctx)->shape) {                                 \
+            HB_EXTRA_SHAPES(STMT)                                   \
+            default: { constexpr int NT_ = HB_V0_NT, CPT_ = HB_V0_CPT, MB_ = HB_V0_MB; constexpr bool FL_ = HB_V0_FULL; STMT; } break; \
+            }                                                       \
+            break;                                                  \
+        }                                                           \
+        HB_OTHER_VARIANTS(ctx, STMT);                               \
+    } while (0)
+#if HB_LEAN
+#define HB_OTHER_VARIANTS(ctx, STMT) do { fprintf(stderr, "[libhydrob200] lean A/B build: 385..416-node grids only\n"); abort(); } while (0)
+#else
+#define HB_OTHER_VARIANTS(ctx, STMT)                                \
+    do {                                                            \
         namespace K = hbr;                                          \
         switch ((ctx)->variant) {                                   \
         case 0: { constexpr int NT_ = HB_V0_NT, CPT_ = HB_V0_CPT, MB_ = HB_V0_MB; constexpr bool FL_ = true; STMT; } break;  \
@@ -287,10 +326,11 @@ static int prep_kernel(hb_ctx *ctx, K kernel, int nt)
         default: { constexpr int NT_ = 512, CPT_ = 3, MB_ = 1; constexpr bool FL_ = false; STMT; } break; \
         }                                                           \
     } while (0)
+#endif
 
 #define DISPATCH_RUN(ctx, FAST_, grid, ...)                                                   \
     do {                                                                                      \
-        HB_FOR_VARIANT(ctx, (K::run_kernel<NT_, CPT_, MB_, FL_, FAST_><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
+        HB_FOR_VARIANT(ctx, (K::run_kernel<NT_, CPT_, MB_, FL_, (FAST_) && !HB_LEAN><<<grid, NT_, (ctx)->smem_bytes, (ctx)->stream>>>(__VA_ARGS__))); \
         (ctx)->launches++;                                                                    \
     } while (0)
 
@@ -332,7 +372,11 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
         if (nx <= 512 && want == 1) ctx->variant = 1;
     }
     ctx->fixed = ctx->variant == 0 && d.nxp == HB_FIXED_NXP && !tuning_env("HB_NO_FIXED");
-    ctx->smem_bytes = smem_doubles(d.nxp, ctx->variant == 0) * sizeof(double);
+    bool full = ctx->variant == 0 && (!ctx->fixed || HB_V0_FULL);
+#if HB_SHAPES
+    if (ctx->fixed) if (const char *v = tuning_env("HB_SHAPE")) { ctx->shape = atoi(v); full = ctx->shape == 0 || ctx->shape == 4; }
+#endif
+    ctx->smem_bytes = smem_doubles(d.nxp, full) * sizeof(double);
     {   // BDF coefficient tables exactly as scipy builds them (bdf.py:244-247)
         const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
         double gam[6], alp[6], erc[6];
@@ -382,6 +426,7 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     { long long *pc; if (dev_alloc(ctx, &pc, 16)) { hb_destroy(ctx); return nullptr; } d.phase_cycles = pc; }
     if (const char *v = tuning_env("HB_CHUNK")) { const int w = atoi(v); if (w > 0) { d.chunk = w; ctx->chunk_fixed = true; } }
     d.dbg = 0; d.fast = 0;
+    d.jac_fuse = tuning_env("HB_JAC_SEQ") ? 0 : 1;   // (A/B and the bit-identity test: one evaluation per group)
 #if HB_DUP_PROBE
     if (const char *v = tuning_env("HB_DBG")) d.dbg = atoi(v);
 #endif
@@ -389,7 +434,7 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
     HB_FOR_VARIANT(ctx, {
         rc = prep_kernel(ctx, K::hook_kernel<NT_, CPT_, MB_, FL_>, NT_);
         if (!rc) rc = prep_kernel(ctx, K::spinup_kernel<NT_, CPT_, MB_, FL_>, NT_);
-        if (!rc) rc = prep_kernel(ctx, K::run_kernel<NT_, CPT_, MB_, FL_, true>, NT_);
+        if (!rc) rc = prep_kernel(ctx, K::run_kernel<NT_, CPT_, MB_, FL_, !HB_LEAN>, NT_);
         if (!rc) rc = prep_kernel(ctx, K::run_kernel<NT_, CPT_, MB_, FL_, false>, NT_);
     });
     if (rc) { hb_destroy(ctx); return nullptr; }

@@ -68,6 +68,7 @@ struct DevCtx {
     int *err_flags;          // [1] HB_ERR_* bits raised by kernels, checked by hb_sync / hb_get_*
     int chunk;               // windows per work item of run_kernel
     int fast;                // HB_FAST_* flags of the fast build of run_kernel (0 in parity mode)
+    int jac_fuse;            // 1: grouped forward differences of the Jacobian in one pass (jac_fused); 0: one evaluation per group
     int dbg;                 // HB_DUP_PROBE builds: bit mask of phases executed twice
     double sqrt_nx;          // sqrt((double)nx), the denominator of the RMS norm
     double newton_tol;       // max(10 eps / rtol, min(0.03, sqrt(rtol)))  (bdf.py:220)
@@ -194,6 +195,18 @@ __constant__ double k_error_const[6];
 //                  fewer spills, fewer address instructions, +8 % measured.
 // ---------------------------------------------------------------------------
 #define HB_FIXED_NXP 416
+// Narrow instances (>= HB_BATCH_MIN_CPT cells per thread) evaluate closures and divisions in
+// batches of independent chains (hb_math.cuh, closure_batch, div_batch).
+#ifndef HB_BATCH_MIN_CPT
+#define HB_BATCH_MIN_CPT 4
+#endif
+#ifndef HB_CLOSURE_BATCH
+#define HB_CLOSURE_BATCH 4
+#endif
+#ifndef HB_CLOSURE_INLINE
+#define HB_CLOSURE_INLINE 0
+#endif
+#include "hb_math.cuh"
 #define HB_IMPL_NS hbr
 #define HB_NXP(c) ((c).nxp)
 #include "hb_device_impl.cuh"

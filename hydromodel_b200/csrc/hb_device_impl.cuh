@@ -79,6 +79,42 @@ __device__ __noinline__ double hb_sqrt(double a) { return sqrt(a); }
 __device__ __noinline__ double hb_exp(double a) { return exp(a); }
 __device__ __noinline__ double hb_log(double a) { return log(a); }
 
+// ---- batches of independent evaluations (narrow instances: >= 4 cells per thread) ----------
+// All main paths of a batch sit in one basic block, so their dependency chains are
+// interleaved by the scheduler; the library functions repeat the whole batch if any
+// element leaves the main path's domain (hb_math.cuh).  Bit-identical to the scalar calls.
+template <int N>
+__device__ __forceinline__ void div_batch(const double *a, const double *b, double *q)
+{
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        bool okr = true;
+        const double v = hbm::div_main(a[r], b[r], okr);
+        // 0 / (finite normal b) = signed zero; exact, but outside the main path's range predicate
+        const int eb = __double2hiint(b[r]) & 0x7ff00000;
+        const bool zero = (a[r] == 0.0) && eb != 0 && eb != 0x7ff00000;
+        q[r] = zero ? __hiloint2double((__double2hiint(a[r]) ^ __double2hiint(b[r])) & 0x80000000, 0) : v;
+        ok = ok && (okr || zero);
+    }
+    if (!ok) {
+#pragma unroll
+        for (int r = 0; r < N; ++r) q[r] = hb_div(a[r], b[r]);
+    }
+}
+// The same for the cells of one thread, at most HB_DIV_CHUNK chains in flight.
+#ifndef HB_DIV_CHUNK
+#define HB_DIV_CHUNK 7
+#endif
+template <int N>
+__device__ __forceinline__ void div_cells(const double *a, const double *b, double *q)
+{
+    if constexpr (N > HB_DIV_CHUNK) {
+        div_batch<HB_DIV_CHUNK>(a, b, q);
+        div_cells<N - HB_DIV_CHUNK>(a + HB_DIV_CHUNK, b + HB_DIV_CHUNK, q + HB_DIV_CHUNK);
+    } else div_batch<N>(a, b, q);
+}
+
 struct Clos { double theta, K, C, kb; };
 
 // Rare branches of the closure, out of line: van Genuchten-Mualem conductivity
@@ -145,6 +181,116 @@ __device__ __noinline__ void closure_cold(const double *par, double psi, double 
                                           double coef, double e, Clos *out)
 {
     *out = closure(par, psi, phi, kmean, coef, e);
+}
+
+// One field of the closure through the scalar code (cold fall-back of closure_batch; returning a
+// scalar keeps the caller's result array in registers).
+__device__ __noinline__ double closure_cold_field(const double *par, double psi, double phi, double kmean,
+                                                  double coef, double e, int field)
+{
+    const Clos r = closure(par, psi, phi, kmean, coef, e);
+    return field == 0 ? r.theta : field == 1 ? r.K : field == 2 ? r.C : r.kb;
+}
+
+// B closure evaluations at once (narrow instances).  Same map and the same operations as
+// closure(), arranged stage by stage over the B elements so that the B dependency chains
+// (log -> exp -> log -> exp -> div -> div -> log -> sqrt -> exp, about 170 dependent FP64
+// operations each) overlap.  Saturated elements are computed on a harmless stand-in argument
+// and replaced by selection, so the batch has no data-dependent branch.  Column-uniform rare
+// cases (van Genuchten conductivity, a general lambda) and any argument outside the main paths
+// of hb_math.cuh go through the scalar code.
+template <int B>
+__device__ __forceinline__ void closure_batch(const double *par, const double (&psi)[B], const double (&phi)[B],
+                                              const double (&kmean)[B], const double (&coef)[B],
+                                              const double (&e)[B], Clos (&out)[B])
+{
+    const double psi_sat = par[HB_P_PSI_SAT], ksoil = par[HB_P_KSAT_SOIL];
+    const bool vg = par[HB_P_MODEL] != 0.0;
+    const double n = par[HB_P_N], m = par[HB_P_M], alpha = par[HB_P_ALPHA];
+    const double th_r = par[HB_P_THETA_RES], lam = par[HB_P_LAMBDA], eps = par[HB_P_EPS];
+    bool ok = !(vg || (lam != 1.0 && lam != 2.0));
+    if (ok) {
+        bool unsat[B];
+        double ax[B], xn[B], base[B], X[B], delta_s[B], one[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            unsat[b] = !(psi[b] >= psi_sat);
+            ax[b] = alpha * fabs(unsat[b] ? psi[b] : -1.0);
+            delta_s[b] = phi[b] - th_r;
+            one[b] = 1.0;
+        }
+        if (n == 2.0) {
+            double sq[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) { xn[b] = ax[b] * ax[b]; base[b] = 1.0 + xn[b]; sq[b] = hbm::sqrt_main(base[b], ok); }
+            div_batch<B>(one, sq, X);
+        } else {
+            double t[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) t[b] = hbm::log_main(ax[b], ok);
+#pragma unroll
+            for (int b = 0; b < B; ++b) { xn[b] = hbm::exp_main(n * t[b], ok); base[b] = 1.0 + xn[b]; }
+#pragma unroll
+            for (int b = 0; b < B; ++b) t[b] = hbm::log_main(base[b], ok);
+#pragma unroll
+            for (int b = 0; b < B; ++b) X[b] = hbm::exp_main(-m * t[b], ok);
+        }
+        double q[B], num[B], s_eff[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) { q[b] = th_r + delta_s[b] * X[b]; num[b] = q[b] - th_r; }
+        div_batch<B>(num, delta_s, s_eff);
+        // background conductivity with the log-normal noise term (logN_rnd, utilities.py:4-54)
+        bool noisy[B];
+        double mean[B], var[B], msq[B], ratio[B], kb[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            s_eff[b] = fmin(fmax(s_eff[b], 0.0), 1.0);
+            noisy[b] = unsat[b] && (coef[b] >= 0.0);
+            mean[b] = (kmean[b] == 0.0) ? 1.0e-7 : kmean[b];
+            var[b] = noisy[b] ? par[HB_P_SIGMA] * (1.0 - s_eff[b]) : 1.0;
+            msq[b] = noisy[b] ? mean[b] * mean[b] : 1.0;
+        }
+        div_batch<B>(var, msq, ratio);
+        double l1[B], sl[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) l1[b] = hbm::log_main(ratio[b] + 1.0, ok);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            bool okr = true;
+            const double v = hbm::sqrt_main(l1[b], okr);
+            sl[b] = (l1[b] == 0.0) ? l1[b] : v;          // sqrt(+-0) = +-0: exact, outside the main path
+            ok = ok && (okr || l1[b] == 0.0);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const double ex = hbm::exp_main(-0.5 * l1[b] + sl[b] * (coef[b] * e[b]), ok);
+            kb[b] = noisy[b] ? mean[b] * ex : ksoil;
+        }
+        double c1[B], c2[B];
+        div_batch<B>(s_eff, base, c1);
+        div_batch<B>(xn, ax, c2);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            double K = ((lam == 1.0) ? s_eff[b] : s_eff[b] * s_eff[b]) * kb[b];
+            K = fmin(K, kb[b]);
+            double C = (m * n) * alpha * delta_s[b] * c1[b] * c2[b];
+            if (C < eps || !isfinite(C)) C = eps;
+            const double kb_sat = (coef[b] >= 0.0) ? kmean[b] : ksoil;
+            out[b].theta = unsat[b] ? q[b] : phi[b];
+            out[b].K = unsat[b] ? K : kb_sat;
+            out[b].C = unsat[b] ? C : eps;
+            out[b].kb = unsat[b] ? kb[b] : kb_sat;
+        }
+    }
+    if (!ok) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            out[b].theta = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 0);
+            out[b].K = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 1);
+            out[b].C = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 2);
+            out[b].kb = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 3);
+        }
+    }
 }
 
 // Arguments of the current window (args_i of simulation.py:591-596 and the t_span of
@@ -410,6 +556,73 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     // The top-boundary closure (bc_fun: (y[0], z = x[0])) rides along as one
     // extra cell of the last thread in the last round, where that thread has no
     // midpoint of its own (nx <= NT*CPT), so the closure code exists only once.
+    if constexpr (CPT >= HB_BATCH_MIN_CPT) {
+    // Narrow instances: the closures of HB_CLOSURE_BATCH "virtual rounds" at a time (closure_batch).
+    // Virtual round 0 is the boundary closure (thread NT-1 alone), virtual round v >= 1 is round
+    // v-1 of the midpoints -- so the boundary rides in the same batch as the unsaturated top of the
+    // column.  A batch without any unsaturated cell in the warp skips the transcendental code.
+    constexpr int B = HB_CLOSURE_BATCH, NVR = CPT + 1;
+#pragma unroll 1
+    for (int v0 = 0; v0 < NVR; v0 += B) {
+        double ym[B], dyn[B], dyd[B], dy[B], e[B], phi[B], km[B], cf[B];
+        bool any_unsat = false;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int v = v0 + b, k = tid + (v - 1) * NT;
+            ym[b] = psi_sat; dyn[b] = 0.0; dyd[b] = 1.0; e[b] = 0.0; phi[b] = 1.0; km[b] = 0.0; cf[b] = 0.0;
+            if (v == 0) {
+                if (tid == NT - 1) {
+                    ym[b] = y[0]; e[b] = nr[0];
+                    phi[b] = par[HB_P_PHI_TOP]; km[b] = par[HB_P_KMEAN_TOP]; cf[b] = par[HB_P_COEF_TOP];
+                }
+            } else if (v < NVR && k < nx - 1) {
+                const double y0 = y[k], y1 = y[k + 1];
+                ym[b] = 0.5 * (y0 + y1);
+                dyn[b] = y1 - y0; dyd[b] = c.dx[k];
+                e[b] = nr[k == 0 ? 0 : k - 1];          // noise index local to the closure's array (quirk Q1)
+                phi[b] = S.phi[k]; km[b] = S.km[k]; cf[b] = S.cf[k];
+            }
+            any_unsat |= !(ym[b] >= psi_sat);
+        }
+        div_batch<B>(dyn, dyd, dy);
+        Clos cl[B];
+        if (__any_sync(HB_FULL, any_unsat)) closure_batch<B>(par, ym, phi, km, cf, e, cl);
+        else {
+            const bool vg = par[HB_P_MODEL] != 0.0;
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                cl[b].theta = phi[b]; cl[b].C = par[HB_P_EPS];
+                cl[b].kb = (!vg && cf[b] >= 0.0) ? km[b] : par[HB_P_KSAT_SOIL];
+                cl[b].K = cl[b].kb;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int v = v0 + b, k = tid + (v - 1) * NT;
+            bool unsat_interior = false;
+            if (v == 0) {
+                if (tid == NT - 1) {
+                    const double q_inf_max = fmin(2.0 * (phi[b] - cl[b].theta) * par[HB_P_DZ], cl[b].kb);
+                    double p_left = 0.0;
+                    if (ym[b] < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(wa[WA_PRECIP]), q_inf_max);
+                    if (mode == 1) p_left -= evaporation(par, ym[b]);
+                    HB_XA(c, NV, X_MISC)[0] = p_left;
+                }
+            } else if (v < NVR && k < nx - 1) {
+                cm[k] = cl[b].C;
+                double fl = cl[b].K * (dy[b] - 1.0);
+                if (hl_on) fl = hydraulic_lift(c, par, col, k, ym[b], dy[b], fl);
+                fm[k] = fl;
+                if (et_on) thm[k] = cl[b].theta;
+                unsat_interior = (k >= 1) && !(ym[b] >= psi_sat);
+            }
+            if (v >= 1 && v < NVR) {
+                const unsigned mask = __ballot_sync(HB_FULL, unsat_interior);
+                if (mask) deepest = max(deepest, (warp << 5) + (v - 1) * NT + (31 - __clz(mask)));
+            }
+        }
+    }
+    } else {
 #pragma unroll 1
     for (int r = 0; r < CPT * HB_DUP(c, 4); ++r) {
         const int k = tid + (r % CPT) * NT;
@@ -428,7 +641,14 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
                 e = nr[k == 0 ? 0 : k - 1];
                 phi = S.phi[k]; km = S.km[k]; cf = S.cf[k];
             }
+#if HB_CLOSURE_INLINE
+            Clos cl1[1];
+            { const double a1[1] = {ym}, a2[1] = {phi}, a3[1] = {km}, a4[1] = {cf}, a5[1] = {e};
+              closure_batch<1>(par, a1, a2, a3, a4, a5, cl1); }
+            const Clos cl = cl1[0];
+#else
             const Clos cl = closure(par, ym, phi, km, cf, e);
+#endif
             if (!bnd) {
                 cm[k] = cl.C;
                 double fl = cl.K * (dy - 1.0);
@@ -446,6 +666,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
         }
         const unsigned mask = __ballot_sync(HB_FULL, unsat_interior);
         if (mask) deepest = max(deepest, (warp << 5) + (r % CPT) * NT + (31 - __clz(mask)));
+    }
     }
     int *wmax = reinterpret_cast<int *>(HB_XA(c, NV, X_WMAX));
     if (lane == 0) wmax[warp] = deepest;
@@ -468,42 +689,58 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     }
     double lat = 0.0;
     double *fo = HB_VEC(c, out);
+    // numerator and denominator of node i (the three node types of richards_pde.py:109-156):
+    //   top     (p_left + (f_0 + zx*s_0)) / (zx*C_0)
+    //   inner   (f_i - f_{i-1} + (zx*s_i + xz*s_{i-1})) / (zx*C_i + xz*C_{i-1})
+    //   bottom  (0 + (f_{n-2} - xz*s_{n-2})) / (-xz*C_{n-2})
+    auto node = [&](int i, double &num, double &den) {
+        const double yi = y[i];
+        // sink at midpoints i and i-1: root uptake (<= 0, daylight) and, inside
+        // the lateral-flow range, min(alpha_lat * psi_mid, sink)
+        double s_i = (et_on && i < nx - 1) ? sk[i] : 0.0, s_m = (et_on && i >= 1) ? sk[i - 1] : 0.0;
+        if (i >= lo && i < hi) {          // own midpoint i
+            s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), s_i);
+            lat += fabs(s_i);
+        }
+        if (i - 1 >= lo && i - 1 < hi)    // midpoint i-1
+            s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), s_m);
+        if (i == 0) {
+            const double zx = c.zx[0];
+            den = zx * cm[0];
+            num = HB_XA(c, NV, X_MISC)[0] + (fm[0] + zx * s_i);
+        } else if (i < nx - 1) {
+            const double zx = c.zx[i], xz = c.xz[i];
+            den = zx * cm[i] + xz * cm[i - 1];
+            num = fm[i] - fm[i - 1] + (zx * s_i + xz * s_m);
+        } else {
+            const double xz = c.xz[i];
+            den = -xz * cm[i - 1];
+            num = 0.0 + (fm[i - 1] - xz * s_m);
+        }
+        if (den == 0.0) den = 1.0;
+    };
+    if constexpr (CPT >= HB_BATCH_MIN_CPT) {
+        double num[CPT], den[CPT], qv[CPT];
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) {
+            const int i = tid + r * NT;
+            num[r] = 0.0; den[r] = 1.0;
+            if (i < nx) node(i, num[r], den[r]);
+        }
+        div_cells<CPT>(num, den, qv);
+#pragma unroll
+        for (int r = 0; r < CPT; ++r) if (const int i = tid + r * NT; i < nx) fo[i] = qv[r];
+    } else {
 #pragma unroll
     for (int r = 0; r < CPT * HB_DUP(c, 8); ++r) {
         const int i = tid + (r % CPT) * NT;
         if (HB_DUP_PROBE && r == CPT) lat = 0.0;
         if (i < nx) {
-            const double yi = y[i];
-            // sink at midpoints i and i-1: root uptake (<= 0, daylight) and, inside
-            // the lateral-flow range, min(alpha_lat * psi_mid, sink)
-            double s_i = (et_on && i < nx - 1) ? sk[i] : 0.0, s_m = (et_on && i >= 1) ? sk[i - 1] : 0.0;
-            if (i >= lo && i < hi) {          // own midpoint i
-                s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), s_i);
-                lat += fabs(s_i);
-            }
-            if (i - 1 >= lo && i - 1 < hi)    // midpoint i-1
-                s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), s_m);
-            // the three node types of richards_pde.py:109-156:
-            //   top     (p_left + (f_0 + zx*s_0)) / (zx*C_0)
-            //   inner   (f_i - f_{i-1} + (zx*s_i + xz*s_{i-1})) / (zx*C_i + xz*C_{i-1})
-            //   bottom  (0 + (f_{n-2} - xz*s_{n-2})) / (-xz*C_{n-2})
             double num, den;
-            if (i == 0) {
-                const double zx = c.zx[0];
-                den = zx * cm[0];
-                num = HB_XA(c, NV, X_MISC)[0] + (fm[0] + zx * s_i);
-            } else if (i < nx - 1) {
-                const double zx = c.zx[i], xz = c.xz[i];
-                den = zx * cm[i] + xz * cm[i - 1];
-                num = fm[i] - fm[i - 1] + (zx * s_i + xz * s_m);
-            } else {
-                const double xz = c.xz[i];
-                den = -xz * cm[i - 1];
-                num = 0.0 + (fm[i - 1] - xz * s_m);
-            }
-            if (den == 0.0) den = 1.0;
+            node(i, num, den);
             fo[i] = hb_div(num, den);
         }
+    }
     }
     lat = warp_sum(lat);
     if (lane == 0) HB_XA(c, NV, X_LATW)[warp] = lat;
@@ -842,21 +1079,21 @@ __device__ __noinline__ void tri_solve(const DevCtx &c, double cc)
 // layout, 385..416 nodes); everything else takes the generic solver (which also
 // does its own back-substitution).
 template <int NV, bool FULL>
-__device__ __forceinline__ bool tri_is13(const DevCtx &c) { return FULL && HB_NXP(c) == 32 * 13; }
+__device__ __forceinline__ bool tri_is13(const DevCtx &c) { return HB_NXP(c) == 32 * 13; }
 template <int NV, bool FULL>
 __device__ __forceinline__ void tri_factor_warp0(const DevCtx &c, double cc)
 {
-    if (FULL && HB_NXP(c) == 32 * 13) tri_factor13<NV>(c, cc); else tri_factor<NV>(c, cc);
+    if (HB_NXP(c) == 32 * 13) tri_factor13<NV>(c, cc); else tri_factor<NV>(c, cc);
 }
 template <int NV, bool FULL>
 __device__ __forceinline__ void tri_solve_warp0(const DevCtx &c, double cc)
 {
-    if (FULL && HB_NXP(c) == 32 * 13) tri_solve13<NV>(c, cc); else tri_solve<NV>(c, cc);
+    if (HB_NXP(c) == 32 * 13) tri_solve13<NV>(c, cc); else tri_solve<NV>(c, cc);
 }
 template <int NV, bool FULL>
 __device__ __forceinline__ double tri_x(const DevCtx &c, int i)
 {
-    if (FULL && HB_NXP(c) == 32 * 13) return tri_x_fixed<NV, 13>(c, i);
+    if (HB_NXP(c) == 32 * 13) return tri_x_fixed<NV, 13>(c, i);
     return HB_VEC(c, V_B)[i];
 }
 
@@ -890,8 +1127,8 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
     const int q = order + 1;
     double *ru = HB_XA(c, NV, X_RU);
     __syncthreads();                       // previous readers of RU are done
-    if (tid < q * q) {
-        const int i = tid / q, j = tid % q;
+    for (int e_ = tid; e_ < q * q; e_ += NT) {     // (NT may be smaller than 36: narrow instances)
+        const int i = e_ / q, j = e_ % q;
         double acc = 0.0;
         for (int k = 0; k < q; ++k) {
             // R[i][k] with `factor`, U[k][j] with 1 (cumulative products down rows)
@@ -952,6 +1189,239 @@ __device__ __forceinline__ void column_stats(const double *fb, const double *fn,
 //   V_JL/V_JD/V_JU un-normalised column differences J[j-1][j], J[j][j], J[j+1][j]
 //   V_PSI max |difference|           V_SCL its scale       V_DD "too small" flag
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// num_jac's grouped forward differences (SCIPY common.py:385-443, first pass over the
+// groups) in ONE pass instead of one right-hand-side evaluation per group.
+//
+// scipy evaluates f(y + h_g) for every colour group g and reads, for each column j of the
+// group, the rows j-1..j+1 of f(y + h_g) - f(y).  Row i of the right-hand side depends on
+// y[i-1..i+1] only (through the midpoints i-1 and i), and same-group columns are at least
+// three apart, so those three rows see exactly ONE perturbed entry, y[j] + h[j].  Midpoint k
+// therefore takes only three different values over all groups: the base one, the one with
+// y[k] perturbed ("L", used by column k) and the one with y[k+1] perturbed ("R", used by
+// column k+1).  The pass evaluates L and R for every midpoint -- two closure evaluations
+// instead of one per group -- and assembles the three rows of every column from them with
+// the same operations rhs_eval uses, so every number is bit-identical to the evaluation per
+// group (tests/test_gpu_round2.py::test_fused_jacobian_is_bit_identical).  The one
+// non-local input, the estimated water table of the lateral-flow sink (deepest unsaturated
+// interior midpoint of the whole perturbed state), is reduced per group.  Rows with the
+// root-water-uptake sink (daylight, ET on: global sums over the profile) keep the
+// evaluation per group, and so does the retry pass with the 10x steps.
+//
+// In:  V_TVL base point, V_TVR steps h, V_TW f(base), cm0 / fm0 = C and flux of the base
+//      evaluation at the midpoints, p_left0 its boundary flux.
+// Out: V_JL/V_JD/V_JU, V_PSI, V_SCL, V_DD exactly as the S_JG state leaves them.
+// Scratch: V_Y (C of L), V_B (flux of L), V_TIP (C of R), G_FAC untouched, one row of the
+// per-CTA global scratch is NOT used; X_PCR (dead while a Jacobian is built).
+// ---------------------------------------------------------------------------
+#define HB_JAC_MAXG 8
+#ifndef HB_JACF_BATCH
+#define HB_JACF_BATCH 0
+#endif
+#ifndef HB_JACF_ATTR
+#define HB_JACF_ATTR __noinline__
+#endif
+template <int NT, int CPT, bool FULL>
+__device__ HB_JACF_ATTR void jac_fused(const DevCtx &c, int col)
+{
+    constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
+    __syncthreads();                                 // the caller's parked controller state is visible
+    // base evaluation: the one at the start of the attempt (C, flux, boundary flux saved by the S_F0
+    // state) for the initial Jacobian, else the one just made by the S_JB state
+    const bool initial = (reinterpret_cast<const int *>(HB_XA(c, NV, X_RU) + 10)[4] & 64) != 0;
+    const double *cm0 = initial ? HB_GROW(c, G_TH) : HB_VEC(c, V_CM);
+    const double *fm0 = initial ? HB_GROW(c, G_SK) : HB_VEC(c, V_FM);
+    const double p_left0 = HB_XA(c, NV, X_MISC)[initial ? 2 : 0];
+    double *fr = HB_VEC(c, V_DD);
+    const Statics S = statics_of<FULL>(c, col);      // (by value here: a reference would pin the caller's copy in local memory)
+    const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ng = c.ng;
+    constexpr int NW = NT / 32;
+    const double *wa = HB_XA(c, NV, X_ARGS);
+    const int mode = (int)wa[WA_MODE];
+    const double *par = HB_XA(c, NV, X_PAR);
+    const double psi_sat = par[HB_P_PSI_SAT];
+    const int flags = (int)par[HB_P_FLAGS];
+    const bool hl_on = (mode == 0) && (flags & HB_FLAG_HLIFT);
+    const double *ybv = HB_VEC(c, V_TVL), *hv = HB_VEC(c, V_TVR), *fbv = HB_VEC(c, V_TW), *nr = HB_VEC(c, V_NR);
+    double *cl_ = HB_VEC(c, V_Y), *fl_ = HB_VEC(c, V_B), *cr = HB_VEC(c, V_TIP);
+    double *jl = HB_VEC(c, V_JL), *jd = HB_VEC(c, V_JD), *ju = HB_VEC(c, V_JU);
+    double *vpsi = HB_VEC(c, V_PSI), *vscl = HB_VEC(c, V_SCL), *vd = HB_VEC(c, V_DD);
+    int *wmaxg = reinterpret_cast<int *>(HB_XA(c, NV, X_PCR));           // [HB_JAC_MAXG][NW <= 16]
+    double *fn0 = HB_XA(c, NV, X_PCR) + 64;                              // f(y + h_g)[0] per group
+    double *plp = HB_XA(c, NV, X_PCR) + 72;                              // boundary flux with y[0] perturbed
+
+    __syncthreads();
+    if (tid < HB_JAC_MAXG) fn0[tid] = fbv[0];
+    // ---- phase 1: the two perturbed evaluations of every midpoint -----------------------
+    int deep[HB_JAC_MAXG];
+#pragma unroll
+    for (int g = 0; g < HB_JAC_MAXG; ++g) deep[g] = -1;
+#pragma unroll 1
+    for (int r = 0; r < CPT; ++r) {
+        const int k = tid + r * NT;
+        bool u0 = false, uL = false, uR = false;
+        int gk = -1, gk1 = -1;
+        if (k < nx - 1) {
+            const double y0 = ybv[k], y1 = ybv[k + 1];
+            const double y0p = y0 + hv[k], y1p = y1 + hv[k + 1];
+            const double e = nr[k == 0 ? 0 : k - 1];
+            const double phi = S.phi[k], km = S.km[k], cf = S.cf[k], dxk = c.dx[k];
+#if HB_JACF_BATCH
+            {   // L (y[k] perturbed) and R (y[k+1] perturbed) as one batch of two independent chains
+                const double ymv[2] = {0.5 * (y0p + y1), 0.5 * (y0 + y1p)}, phv[2] = {phi, phi}, kmv[2] = {km, km},
+                             cfv[2] = {cf, cf}, ev[2] = {e, e};
+                const double dn[2] = {y1 - y0p, y1p - y0}, dd2[2] = {dxk, dxk};
+                double dyv[2];
+                div_batch<2>(dn, dd2, dyv);
+                Clos cl[2];
+                closure_batch<2>(par, ymv, phv, kmv, cfv, ev, cl);
+                double flL = cl[0].K * (dyv[0] - 1.0), flR = cl[1].K * (dyv[1] - 1.0);
+                if (hl_on) { flL = hydraulic_lift(c, par, col, k, ymv[0], dyv[0], flL); flR = hydraulic_lift(c, par, col, k, ymv[1], dyv[1], flR); }
+                cl_[k] = cl[0].C; fl_[k] = flL; cr[k] = cl[1].C; fr[k] = flR;
+                uL = (k >= 1) && !(ymv[0] >= psi_sat); uR = (k >= 1) && !(ymv[1] >= psi_sat);
+            }
+#else
+            {   // L: y[k] perturbed
+                const double ym = 0.5 * (y0p + y1), dy = hb_div(y1 - y0p, dxk);
+                const Clos cl = closure(par, ym, phi, km, cf, e);
+                double fl = cl.K * (dy - 1.0);
+                if (hl_on) fl = hydraulic_lift(c, par, col, k, ym, dy, fl);
+                cl_[k] = cl.C; fl_[k] = fl;
+                uL = (k >= 1) && !(ym >= psi_sat);
+            }
+            {   // R: y[k+1] perturbed
+                const double ym = 0.5 * (y0 + y1p), dy = hb_div(y1p - y0, dxk);
+                const Clos cl = closure(par, ym, phi, km, cf, e);
+                double fl = cl.K * (dy - 1.0);
+                if (hl_on) fl = hydraulic_lift(c, par, col, k, ym, dy, fl);
+                cr[k] = cl.C; fr[k] = fl;
+                uR = (k >= 1) && !(ym >= psi_sat);
+            }
+#endif
+            u0 = (k >= 1) && !(0.5 * (y0 + y1) >= psi_sat);
+            gk = c.grp[k]; gk1 = c.grp[k + 1];
+        }
+        // deepest unsaturated interior midpoint of the state perturbed by group g
+#pragma unroll
+        for (int g = 0; g < HB_JAC_MAXG; ++g) {
+            if (g < ng) {
+                const bool u = (gk == g) ? uL : (gk1 == g) ? uR : u0;
+                const unsigned mask = __ballot_sync(HB_FULL, u);
+                if (mask) deep[g] = max(deep[g], (warp << 5) + r * NT + (31 - __clz(mask)));
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < HB_JAC_MAXG; ++g) wmaxg[g * 16 + warp] = deep[g];
+    }
+    if (tid == NT - 1) {
+        // boundary closure with y[0] perturbed (bc_fun, as in rhs_eval)
+        const double ym = ybv[0] + hv[0];
+        const double phi = par[HB_P_PHI_TOP];
+        const Clos cl = closure(par, ym, phi, par[HB_P_KMEAN_TOP], par[HB_P_COEF_TOP], nr[0]);
+        const double q_inf_max = fmin(2.0 * (phi - cl.theta) * par[HB_P_DZ], cl.kb);
+        double p_left = 0.0;
+        if (ym < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(wa[WA_PRECIP]), q_inf_max);
+        if (mode == 1) p_left -= evaporation(par, ym);
+        plp[0] = p_left;
+    }
+    __syncthreads();
+
+    // ---- phase 2a: rows j-1, j, j+1 of f(y + h_g) for every column j (g = its group) ------
+#pragma unroll 1
+    for (int r = 0; r < CPT; ++r) {
+        const int j = tid + r * NT;
+        if (j >= nx) continue;
+        const int g = c.grp[j];
+        int lo = 1, hi = 0;                  // active range of the lateral-flow sink: [lo, hi)
+        if (flags & HB_FLAG_LF) {
+            int kmax = wmaxg[g * 16];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) kmax = max(kmax, wmaxg[g * 16 + w]);
+            const int dim_d = nx - 2;
+            const int wtd_obs = min((int)wa[WA_WTD], dim_d - 1);
+            const int wtd_est = (kmax < 0) ? 0 : min(kmax, dim_d - 1);
+            if (wtd_est < wtd_obs) { lo = wtd_est + 1; hi = wtd_obs + 1; }
+        }
+        const double yjp = ybv[j] + hv[j];
+        double f3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int i = j - 1 + q;
+            if (i < 0 || i >= nx) continue;
+            // state, C and flux as row i sees them: y[j], midpoint j (L) and midpoint j-1 (R) perturbed
+            const double yi = (q == 1) ? yjp : ybv[i];
+            double s_i = 0.0, s_m = 0.0;
+            if (i >= lo && i < hi) {
+                const double ynext = (q == 0) ? yjp : ybv[i + 1];
+                s_i = fmin(-2.5e-4 * (0.5 * (yi + ynext)), s_i);
+            }
+            if (i - 1 >= lo && i - 1 < hi) {
+                const double yprev = (q == 2) ? yjp : ybv[i - 1];
+                s_m = fmin(-2.5e-4 * (0.5 * (yprev + yi)), s_m);
+            }
+            // midpoint i:   q == 0 -> j-1 (R), q == 1 -> j (L), q == 2 -> j+1 (base)
+            // midpoint i-1: q == 0 -> j-2 (base), q == 1 -> j-1 (R), q == 2 -> j (L)
+            double num, den;
+            if (i == 0) {
+                const double zx = c.zx[0];
+                const double cmi = (q == 0) ? cr[0] : cl_[0], fmi = (q == 0) ? fr[0] : fl_[0];
+                den = zx * cmi;
+                num = ((j == 0) ? plp[0] : p_left0) + (fmi + zx * s_i);
+            } else if (i < nx - 1) {
+                const double zx = c.zx[i], xz = c.xz[i];
+                const double cmi = (q == 0) ? cr[i] : (q == 1) ? cl_[i] : cm0[i];
+                const double fmi = (q == 0) ? fr[i] : (q == 1) ? fl_[i] : fm0[i];
+                const double cmm = (q == 0) ? cm0[i - 1] : (q == 1) ? cr[i - 1] : cl_[i - 1];
+                const double fmm = (q == 0) ? fm0[i - 1] : (q == 1) ? fr[i - 1] : fl_[i - 1];
+                den = zx * cmi + xz * cmm;
+                num = fmi - fmm + (zx * s_i + xz * s_m);
+            } else {
+                const double xz = c.xz[i];
+                const double cmm = (q == 1) ? cr[i - 1] : cl_[i - 1];
+                const double fmm = (q == 1) ? fr[i - 1] : fl_[i - 1];
+                den = -xz * cmm;
+                num = 0.0 + (fmm - xz * s_m);
+            }
+            if (den == 0.0) den = 1.0;
+            f3[q] = hb_div(num, den);
+        }
+        jl[j] = f3[0]; jd[j] = f3[1]; ju[j] = f3[2];
+        if (j == 0) fn0[g] = f3[1];
+        if (j == 1) fn0[g] = f3[0];
+    }
+    __syncthreads();
+
+    // ---- phase 2b: column statistics with scipy's sparse-argmax semantics (column_stats) ---
+    const double REJECT = 2.0097183471152322e-14;     // EPS ** 0.875
+#pragma unroll 1
+    for (int r = 0; r < CPT; ++r) {
+        const int j = tid + r * NT;
+        if (j >= nx) continue;
+        const int lo_r = j > 0 ? j - 1 : 0, hi_r = j < nx - 1 ? j + 1 : nx - 1;
+        const double fnv3[3] = {jl[j], jd[j], ju[j]};
+        double dv[3] = {0.0, 0.0, 0.0};
+        int best = lo_r; double bv = -1.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int i = j - 1 + q;
+            if (i < lo_r || i > hi_r) continue;
+            dv[q] = fnv3[q] - fbv[i];
+            const double v = fabs(dv[q]);
+            if (i == lo_r || v > bv) { bv = v; best = i; }
+        }
+        double maxd, fb_mi, fn_mi;
+        if (bv > 0.0) { maxd = bv; fb_mi = fbv[best]; fn_mi = (best == j - 1) ? fnv3[0] : (best == j) ? fnv3[1] : fnv3[2]; }
+        else { fb_mi = fbv[0]; fn_mi = fn0[c.grp[j]]; maxd = (lo_r == 0) ? fabs(fn_mi - fb_mi) : 0.0; }
+        const double scl = fmax(fabs(fb_mi), fabs(fn_mi));
+        jl[j] = (j > 0) ? dv[0] : 0.0; jd[j] = dv[1]; ju[j] = (j < nx - 1) ? dv[2] : 0.0;
+        vpsi[j] = maxd; vscl[j] = scl;
+        vd[j] = (maxd < REJECT * scl) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+}
+
 // Fast mode only (never the default): what one window hands to the next
 // one of the same column inside a chunk of rows.
 struct Warm {
@@ -966,10 +1436,16 @@ struct Warm {
 
 template <int NT, int CPT, bool FULL, bool FAST = false>
 __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
-                                        const double *y_glob, int jac_only = 0, Warm *warm = nullptr)
+                                        const double *y_glob, int jac_only = 0, Warm *warm = nullptr,
+                                        bool after_jac = false)
 {
     // jac_only (test hook): 1 = return after the initial Jacobian, 2 = the same
     // but starting from the step factors already in the G_FAC scratch row.
+    // Return value 2 = "grouped differences wanted": the caller runs jac_fused() and calls again with
+    // after_jac = true (bdf_solve below).  The pass is called from out there and not from inside the
+    // integrator loop because a call of a large function in here makes the register allocator keep half
+    // of the controller state in local memory for the WHOLE loop (measured: spill traffic doubled, -8 %);
+    // the controller state crosses the gap parked in shared memory.
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     enum { S_F0, S_F1, S_JB, S_JG, S_JR, S_NW };
     enum { GO_NONE, GO_JAC_END, GO_STEP_BEGIN, GO_STEP_RETRY, GO_PREDICT, GO_NEWTON_BEGIN,
@@ -991,10 +1467,48 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     int state = S_F0, order = 1, n_equal = 0, k_newton = 0, jac_g = 0;
     bool lu_valid = false, current_jac = false, have_old = false, jac_first = true, jac_init = true;
     bool any_accept = false;                        // a step of THIS attempt has been accepted
+    // grouped forward differences of the Jacobian in one pass (jac_fused) unless the root-uptake
+    // sink is active in this window (its global sums need the evaluation per group)
+    // (recomputed where it is needed: nothing of it stays live across the integrator loop)
+#define HB_JAC_FUSE(c, NV, wa) ((c).jac_fuse && !((int)(wa)[WA_MODE] == 1 && ((int)HB_XA(c, NV, X_PAR)[HB_P_FLAGS] & HB_FLAG_ET)))
     double t = wa[WA_T0], t_new = t, h_abs = 0.0, h_loc = 0.0, min_step = 0.0, cc = 0.0, c_lu = 0.0;
     double dy_norm_old = 0.0, d1_init = 0.0, h0_init = 0.0;
 
+    double *ctl = HB_XA(c, NV, X_RU);               // parked controller state (change_D's matrix is dead then)
+    int *cti = reinterpret_cast<int *>(ctl + 10);
+    int go = GO_NONE;
+    bool jb_now = false;
     __syncthreads();
+    if (after_jac) {
+        // ---- back from jac_fused: the differences of all first-pass groups are in place -----------
+        t = ctl[0]; t_new = ctl[1]; h_abs = ctl[2]; h_loc = ctl[3]; min_step = ctl[4]; cc = ctl[5];
+        c_lu = ctl[6]; dy_norm_old = ctl[7]; d1_init = ctl[8]; h0_init = ctl[9];
+        order = cti[0]; n_equal = cti[1]; k_newton = cti[2]; par_ = cti[3];
+        { const int fl = cti[4]; lu_valid = fl & 1; current_jac = fl & 2; have_old = fl & 4; jac_first = fl & 8;
+          jac_init = fl & 16; any_accept = fl & 32; }
+        // what the S_JG branch does after its last group: the retry pass over the groups that hold a
+        // column whose difference was too small (10x step), one evaluation per group
+        int want = c.ng;
+        if (!FAST) {                                    // (fast mode has no retry pass)
+            for (int j = tid; j < nx; j += NT)
+                if (vd[j] != 0.0) want = min(want, c.grp[j]);
+            want = -block_max_int<NT, NV>(c, par_, -want);
+        }
+        state = S_JG;
+        if (want >= c.ng) go = GO_JAC_END;
+        else {
+            HB_FOR_CELLS(i) {
+                double step = 0.0;
+                if (c.grp[i] == want && vd[i] != 0.0) {
+                    const double ybi = ybv[i];
+                    const double ysc = ((fbv[i] >= 0.0) ? 1.0 : -1.0) * fmax(atol, fabs(ybi));
+                    step = (ybi + 10.0 * fac[i] * ysc) - ybi;
+                }
+                y[i] = ybv[i] + step;
+            }
+            jac_g = want; state = S_JR;
+        }
+    } else
     // __ldcg: the state may have been written by another SM (time-sliced columns)
     if (!(FAST && warm->valid && warm->cont))
         for (int i = tid; i < nx; i += NT) { const double v = __ldcg(y_glob + i); y[i] = v; D[i] = v; }
@@ -1005,15 +1519,17 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     // t_bound -- no select_initial_step, no new Jacobian, no restart at order 1 (what scipy does
     // at every solve_ivp call, bdf.py:198-241, ivp.py:582-660).
     bool resume = false;
-    if (FAST) {
+    if (FAST && !after_jac) {
         resume = warm->valid && warm->cont;
         if (resume) { order = warm->order; n_equal = warm->n_equal; h_abs = warm->h; t = wa[WA_T0]; }
         warm->valid = false;
     }
 
+    // (re-entry after jac_fused: into the loop behind the evaluation, with `go` as set above)
+    if (after_jac) goto behind_eval;
     for (;;) {
-        int go = GO_NONE;
-        bool jb_now = false;
+        go = GO_NONE;
+        jb_now = false;
         if (FAST && resume) { resume = false; go = GO_STEP_BEGIN; }
         else {
         // ======== the single right-hand-side evaluation ========================
@@ -1063,6 +1579,21 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     for (int i = tid; i < nx; i += NT) { const double dy = b[i]; const double q = hb_div(dy, vscl[i]); loc += q * q; s1[i] = y[i] + dy; s2[i] = vd[i] + dy; }
                     loc = 0.0; }
 #endif
+                if constexpr (CPT >= HB_BATCH_MIN_CPT) {
+                    double dyv[CPT], scv[CPT], qv[CPT];
+#pragma unroll
+                    for (int r_ = 0; r_ < CPT; ++r_) {
+                        const int i = tid + r_ * NT;
+                        dyv[r_] = 0.0; scv[r_] = 1.0;
+                        if (i < nx) { dyv[r_] = tri_x<NV, FULL>(c, i); scv[r_] = vscl[i]; }
+                    }
+                    div_cells<CPT>(dyv, scv, qv);
+                    HB_FOR_CELLS(i) {
+                        loc += qv[r_] * qv[r_];
+                        y[i] += dyv[r_];               // tentative: discarded if we stop
+                        vd[i] += dyv[r_];
+                    }
+                } else
                 HB_FOR_CELLS(i) {
                     const double dy = tri_x<NV, FULL>(c, i);
                     const double q = hb_div(dy, vscl[i]);
@@ -1114,6 +1645,21 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                 const double safety = 0.9 * (2 * HB_NEWTON_MAXITER + 1) /
                                       (double)(2 * HB_NEWTON_MAXITER + n_iter);
                 double le = 0.0;
+                if constexpr (CPT >= HB_BATCH_MIN_CPT) {
+                    double nv[CPT], scv[CPT], qv[CPT];
+#pragma unroll
+                    for (int r_ = 0; r_ < CPT; ++r_) {
+                        const int i = tid + r_ * NT;
+                        nv[r_] = 0.0; scv[r_] = 1.0;
+                        if (i < nx) {
+                            scv[r_] = atol + rtol * fabs(y[i]);
+                            vscl[i] = scv[r_];
+                            nv[r_] = k_error_const[order] * vd[i];
+                        }
+                    }
+                    div_cells<CPT>(nv, scv, qv);
+                    HB_FOR_CELLS(i) le += qv[r_] * qv[r_];
+                } else
                 for (int rp_ = 0; rp_ < HB_DUP(c, 512); ++rp_) { le = 0.0;
                 HB_FOR_CELLS(i) {
                     const double sc = atol + rtol * fabs(y[i]);
@@ -1151,6 +1697,39 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     if (c.dbg & 2048) change_D<NT, CPT, NV>(c, order, 1.0);
 #endif
                     double lm = 0.0, lp = 0.0;
+                    if constexpr (CPT >= HB_BATCH_MIN_CPT) {
+                        // (the rows of the table in the outer loop, the thread's cells unrolled inside:
+                        // the loads of a row are independent of one another)
+                        double nm[CPT], np_[CPT], scv[CPT], qm[CPT], qp[CPT], acc[CPT];
+#pragma unroll
+                        for (int r_ = 0; r_ < CPT; ++r_) {
+                            const int i = tid + r_ * NT;
+                            nm[r_] = 0.0; np_[r_] = 0.0; scv[r_] = 1.0; acc[r_] = 0.0;
+                            if (i < nx) {
+                                const double di = vd[i];
+                                const double dlast = di - D[(order + 1) * nxp + i];
+                                D[(order + 2) * nxp + i] = dlast;
+                                D[(order + 1) * nxp + i] = di;
+                                acc[r_] = di;
+                                np_[r_] = k_error_const[order < HB_MAX_ORDER ? order + 1 : 0] * dlast;
+                                scv[r_] = vscl[i];
+                            }
+                        }
+                        for (int kk = order; kk >= 0; --kk) {
+                            HB_FOR_CELLS(i) {
+                                acc[r_] = D[kk * nxp + i] + acc[r_];
+                                D[kk * nxp + i] = acc[r_];
+                            }
+                            if (kk == order) {
+#pragma unroll
+                                for (int r_ = 0; r_ < CPT; ++r_) nm[r_] = k_error_const[order > 1 ? order - 1 : 0] * acc[r_];
+                            }
+                        }
+                        if (decide) {
+                            if (order > 1) { div_cells<CPT>(nm, scv, qm); HB_FOR_CELLS(i) lm += qm[r_] * qm[r_]; }
+                            if (order < HB_MAX_ORDER) { div_cells<CPT>(np_, scv, qp); HB_FOR_CELLS(i) lp += qp[r_] * qp[r_]; }
+                        }
+                    } else
                     HB_FOR_CELLS(i) {
                         const double di = vd[i];
                         D[(order + 2) * nxp + i] = di - D[(order + 1) * nxp + i];
@@ -1208,6 +1787,13 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
             const double h0 = (d0 < 1e-5 || d1_init < 1e-5) ? 1e-6 : 0.01 * d0 / d1_init;
             h0_init = fmin(h0, fabs(wa[WA_TBOUND] - wa[WA_T0]));
             for (int i = tid; i < nx; i += NT) y[i] = D[i] + h0_init * D[nxp + i];
+            if (HB_JAC_FUSE(c, NV, wa)) {
+                // C, flux and boundary flux of this evaluation at y0: the base values of the
+                // initial Jacobian (the evaluation of the S_F1 state overwrites V_CM / V_FM)
+                double *cm_s = HB_GROW(c, G_TH), *fm_s = HB_GROW(c, G_SK);
+                for (int i = tid; i < nx - 1; i += NT) { cm_s[i] = HB_VEC(c, V_CM)[i]; fm_s[i] = HB_VEC(c, V_FM)[i]; }
+                if (tid == 0) HB_XA(c, NV, X_MISC)[2] = HB_XA(c, NV, X_MISC)[0];
+            }
             state = S_F1;
         } else if (state == S_F1) {
             // ---- select_initial_step, second half (common.py:116-134) ---------
@@ -1283,6 +1869,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         }
 
         }   // (not resuming)
+behind_eval:
 
         if (jb_now) {
             // ---- num_jac: steps from the base value (common.py:320-341) -------
@@ -1296,8 +1883,20 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                 vd[i] = 0.0;
                 y[i] = ybi + ((c.grp[i] == 0) ? h : 0.0);
             }
-            jac_g = 0;
-            state = S_JG;
+            if (HB_JAC_FUSE(c, NV, wa)) {
+                // park the controller state and hand over to jac_fused (see the head of this function)
+                const bool initial = (state == S_F1);          // base evaluation: the S_F0 one (saved) or the S_JB one
+                __syncthreads();
+                if (tid == 0) {
+                    ctl[0] = t; ctl[1] = t_new; ctl[2] = h_abs; ctl[3] = h_loc; ctl[4] = min_step; ctl[5] = cc;
+                    ctl[6] = c_lu; ctl[7] = dy_norm_old; ctl[8] = d1_init; ctl[9] = h0_init;
+                    cti[0] = order; cti[1] = n_equal; cti[2] = k_newton; cti[3] = par_;
+                    cti[4] = (lu_valid ? 1 : 0) | (current_jac ? 2 : 0) | (have_old ? 4 : 0) | (jac_first ? 8 : 0) |
+                             (jac_init ? 16 : 0) | (any_accept ? 32 : 0) | (initial ? 64 : 0);
+                    cnt[K_NRHS] += c.ng;                       // the evaluations scipy makes (one per group)
+                }
+                return 2;
+            } else { jac_g = 0; state = S_JG; }
         }
 
         if (go == GO_JAC_END) {
@@ -1374,6 +1973,29 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
             // ---- predictor, scale, psi (bdf.py:360-366) ----------------------
             cc = hb_div(t_new - t, k_alpha[order]);
             __syncthreads();
+            if constexpr (CPT >= HB_BATCH_MIN_CPT) {
+                double psv[CPT], alv[CPT], qv[CPT], acc[CPT];
+#pragma unroll
+                for (int r_ = 0; r_ < CPT; ++r_) {
+                    const int i = tid + r_ * NT;
+                    psv[r_] = 0.0; alv[r_] = k_alpha[order];
+                    acc[r_] = (i < nx) ? D[i] : 0.0;
+                }
+                for (int kk = 1; kk <= order; ++kk) {
+                    const double gk = k_gamma[kk];
+                    HB_FOR_CELLS(i) {
+                        const double dk = D[kk * nxp + i];
+                        acc[r_] += dk; psv[r_] += dk * gk;
+                    }
+                }
+                div_cells<CPT>(psv, alv, qv);
+                HB_FOR_CELLS(i) {
+                    y[i] = acc[r_];
+                    vscl[i] = atol + rtol * fabs(acc[r_]);
+                    vd[i] = 0.0;
+                    vpsi[i] = qv[r_];
+                }
+            } else
             for (int rp_ = 0; rp_ < HB_DUP(c, 32); ++rp_)
             HB_FOR_CELLS(i) {
                 double acc = D[i], ps = 0.0;
@@ -1410,6 +2032,19 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     }
 }
 
+// One solve_ivp call: bdf_attempt with the grouped Jacobian differences made out here.
+template <int NT, int CPT, bool FULL, bool FAST = false>
+__device__ __forceinline__ int bdf_solve(const DevCtx &c, int col, const double *y_glob, int jac_only = 0,
+                                         Warm *warm = nullptr)
+{
+    int st = bdf_attempt<NT, CPT, FULL, FAST>(c, col, y_glob, jac_only, warm, false);
+    while (st == 2) {
+        jac_fused<NT, CPT, FULL>(c, col);
+        st = bdf_attempt<NT, CPT, FULL, FAST>(c, col, y_glob, jac_only, warm, true);
+    }
+    return st;
+}
+
 // RichardsPDE.solve (richards_pde.py:478-537): up to 5 attempts, the noise
 // field damped in place by 0.8 after each failure (quirk Q4); the state of the
 // last attempt is left in V_Y (quirk Q5).  Returns 0 ok / 1 failed.
@@ -1421,7 +2056,7 @@ __device__ inline int solve_window(const DevCtx &c, int col, const Args &a, doub
     int trials = HB_N_TRIALS, status = 0;
     set_window_args<NV>(c, a, t0, t1);
     while (trials > 0) {
-        status = bdf_attempt<NT, CPT, FULL, FAST>(c, col, y_glob, 0, warm);
+        status = bdf_solve<NT, CPT, FULL, FAST>(c, col, y_glob, 0, warm);
         if (status == 0) break;
         for (int i = threadIdx.x; i < c.nx; i += NT) HB_VEC(c, V_NR)[i] *= HB_NOISE_DAMP;
         noise_damped = true;

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NT, MB) hook_kernel(const __grid_constant__ De
         // the production state machine, stopped right after the initial Jacobian
         if (!h.first) for (int i = tid; i < nx; i += NT) HB_GROW(c, G_FAC)[i] = io[2 * nx + i];
         set_window_args<NV>(c, a, 0.0, 1.0);
-        bdf_attempt<NT, CPT, FULL>(c, h.col, io, h.first ? 1 : 2);
+        bdf_solve<NT, CPT, FULL>(c, h.col, io, h.first ? 1 : 2);
         for (int i = tid; i < nx; i += NT) {
             io[3 * nx + i] = HB_VEC(c, V_JL)[i]; io[4 * nx + i] = HB_VEC(c, V_JD)[i];
             io[5 * nx + i] = HB_VEC(c, V_JU)[i]; io[6 * nx + i] = HB_GROW(c, G_FAC)[i];
