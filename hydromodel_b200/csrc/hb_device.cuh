@@ -195,18 +195,6 @@ __constant__ double k_error_const[6];
 //                  fewer spills, fewer address instructions, +8 % measured.
 // ---------------------------------------------------------------------------
 #define HB_FIXED_NXP 416
-// Narrow instances (>= HB_BATCH_MIN_CPT cells per thread) evaluate closures and divisions in
-// batches of independent chains (hb_math.cuh, closure_batch, div_batch).
-#ifndef HB_BATCH_MIN_CPT
-#define HB_BATCH_MIN_CPT 4
-#endif
-#ifndef HB_CLOSURE_BATCH
-#define HB_CLOSURE_BATCH 4
-#endif
-#ifndef HB_CLOSURE_INLINE
-#define HB_CLOSURE_INLINE 0
-#endif
-#include "hb_math.cuh"
 #define HB_IMPL_NS hbr
 #define HB_NXP(c) ((c).nxp)
 #include "hb_device_impl.cuh"

@@ -79,42 +79,6 @@ __device__ __noinline__ double hb_sqrt(double a) { return sqrt(a); }
 __device__ __noinline__ double hb_exp(double a) { return exp(a); }
 __device__ __noinline__ double hb_log(double a) { return log(a); }
 
-// ---- batches of independent evaluations (narrow instances: >= 4 cells per thread) ----------
-// All main paths of a batch sit in one basic block, so their dependency chains are
-// interleaved by the scheduler; the library functions repeat the whole batch if any
-// element leaves the main path's domain (hb_math.cuh).  Bit-identical to the scalar calls.
-template <int N>
-__device__ __forceinline__ void div_batch(const double *a, const double *b, double *q)
-{
-    bool ok = true;
-#pragma unroll
-    for (int r = 0; r < N; ++r) {
-        bool okr = true;
-        const double v = hbm::div_main(a[r], b[r], okr);
-        // 0 / (finite normal b) = signed zero; exact, but outside the main path's range predicate
-        const int eb = __double2hiint(b[r]) & 0x7ff00000;
-        const bool zero = (a[r] == 0.0) && eb != 0 && eb != 0x7ff00000;
-        q[r] = zero ? __hiloint2double((__double2hiint(a[r]) ^ __double2hiint(b[r])) & 0x80000000, 0) : v;
-        ok = ok && (okr || zero);
-    }
-    if (!ok) {
-#pragma unroll
-        for (int r = 0; r < N; ++r) q[r] = hb_div(a[r], b[r]);
-    }
-}
-// The same for the cells of one thread, at most HB_DIV_CHUNK chains in flight.
-#ifndef HB_DIV_CHUNK
-#define HB_DIV_CHUNK 7
-#endif
-template <int N>
-__device__ __forceinline__ void div_cells(const double *a, const double *b, double *q)
-{
-    if constexpr (N > HB_DIV_CHUNK) {
-        div_batch<HB_DIV_CHUNK>(a, b, q);
-        div_cells<N - HB_DIV_CHUNK>(a + HB_DIV_CHUNK, b + HB_DIV_CHUNK, q + HB_DIV_CHUNK);
-    } else div_batch<N>(a, b, q);
-}
-
 struct Clos { double theta, K, C, kb; };
 
 // Rare branches of the closure, out of line: van Genuchten-Mualem conductivity
@@ -181,116 +145,6 @@ __device__ __noinline__ void closure_cold(const double *par, double psi, double 
                                           double coef, double e, Clos *out)
 {
     *out = closure(par, psi, phi, kmean, coef, e);
-}
-
-// One field of the closure through the scalar code (cold fall-back of closure_batch; returning a
-// scalar keeps the caller's result array in registers).
-__device__ __noinline__ double closure_cold_field(const double *par, double psi, double phi, double kmean,
-                                                  double coef, double e, int field)
-{
-    const Clos r = closure(par, psi, phi, kmean, coef, e);
-    return field == 0 ? r.theta : field == 1 ? r.K : field == 2 ? r.C : r.kb;
-}
-
-// B closure evaluations at once (narrow instances).  Same map and the same operations as
-// closure(), arranged stage by stage over the B elements so that the B dependency chains
-// (log -> exp -> log -> exp -> div -> div -> log -> sqrt -> exp, about 170 dependent FP64
-// operations each) overlap.  Saturated elements are computed on a harmless stand-in argument
-// and replaced by selection, so the batch has no data-dependent branch.  Column-uniform rare
-// cases (van Genuchten conductivity, a general lambda) and any argument outside the main paths
-// of hb_math.cuh go through the scalar code.
-template <int B>
-__device__ __forceinline__ void closure_batch(const double *par, const double (&psi)[B], const double (&phi)[B],
-                                              const double (&kmean)[B], const double (&coef)[B],
-                                              const double (&e)[B], Clos (&out)[B])
-{
-    const double psi_sat = par[HB_P_PSI_SAT], ksoil = par[HB_P_KSAT_SOIL];
-    const bool vg = par[HB_P_MODEL] != 0.0;
-    const double n = par[HB_P_N], m = par[HB_P_M], alpha = par[HB_P_ALPHA];
-    const double th_r = par[HB_P_THETA_RES], lam = par[HB_P_LAMBDA], eps = par[HB_P_EPS];
-    bool ok = !(vg || (lam != 1.0 && lam != 2.0));
-    if (ok) {
-        bool unsat[B];
-        double ax[B], xn[B], base[B], X[B], delta_s[B], one[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            unsat[b] = !(psi[b] >= psi_sat);
-            ax[b] = alpha * fabs(unsat[b] ? psi[b] : -1.0);
-            delta_s[b] = phi[b] - th_r;
-            one[b] = 1.0;
-        }
-        if (n == 2.0) {
-            double sq[B];
-#pragma unroll
-            for (int b = 0; b < B; ++b) { xn[b] = ax[b] * ax[b]; base[b] = 1.0 + xn[b]; sq[b] = hbm::sqrt_main(base[b], ok); }
-            div_batch<B>(one, sq, X);
-        } else {
-            double t[B];
-#pragma unroll
-            for (int b = 0; b < B; ++b) t[b] = hbm::log_main(ax[b], ok);
-#pragma unroll
-            for (int b = 0; b < B; ++b) { xn[b] = hbm::exp_main(n * t[b], ok); base[b] = 1.0 + xn[b]; }
-#pragma unroll
-            for (int b = 0; b < B; ++b) t[b] = hbm::log_main(base[b], ok);
-#pragma unroll
-            for (int b = 0; b < B; ++b) X[b] = hbm::exp_main(-m * t[b], ok);
-        }
-        double q[B], num[B], s_eff[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) { q[b] = th_r + delta_s[b] * X[b]; num[b] = q[b] - th_r; }
-        div_batch<B>(num, delta_s, s_eff);
-        // background conductivity with the log-normal noise term (logN_rnd, utilities.py:4-54)
-        bool noisy[B];
-        double mean[B], var[B], msq[B], ratio[B], kb[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            s_eff[b] = fmin(fmax(s_eff[b], 0.0), 1.0);
-            noisy[b] = unsat[b] && (coef[b] >= 0.0);
-            mean[b] = (kmean[b] == 0.0) ? 1.0e-7 : kmean[b];
-            var[b] = noisy[b] ? par[HB_P_SIGMA] * (1.0 - s_eff[b]) : 1.0;
-            msq[b] = noisy[b] ? mean[b] * mean[b] : 1.0;
-        }
-        div_batch<B>(var, msq, ratio);
-        double l1[B], sl[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) l1[b] = hbm::log_main(ratio[b] + 1.0, ok);
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            bool okr = true;
-            const double v = hbm::sqrt_main(l1[b], okr);
-            sl[b] = (l1[b] == 0.0) ? l1[b] : v;          // sqrt(+-0) = +-0: exact, outside the main path
-            ok = ok && (okr || l1[b] == 0.0);
-        }
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const double ex = hbm::exp_main(-0.5 * l1[b] + sl[b] * (coef[b] * e[b]), ok);
-            kb[b] = noisy[b] ? mean[b] * ex : ksoil;
-        }
-        double c1[B], c2[B];
-        div_batch<B>(s_eff, base, c1);
-        div_batch<B>(xn, ax, c2);
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            double K = ((lam == 1.0) ? s_eff[b] : s_eff[b] * s_eff[b]) * kb[b];
-            K = fmin(K, kb[b]);
-            double C = (m * n) * alpha * delta_s[b] * c1[b] * c2[b];
-            if (C < eps || !isfinite(C)) C = eps;
-            const double kb_sat = (coef[b] >= 0.0) ? kmean[b] : ksoil;
-            out[b].theta = unsat[b] ? q[b] : phi[b];
-            out[b].K = unsat[b] ? K : kb_sat;
-            out[b].C = unsat[b] ? C : eps;
-            out[b].kb = unsat[b] ? kb[b] : kb_sat;
-        }
-    }
-    if (!ok) {
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            out[b].theta = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 0);
-            out[b].K = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 1);
-            out[b].C = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 2);
-            out[b].kb = closure_cold_field(par, psi[b], phi[b], kmean[b], coef[b], e[b], 3);
-        }
-    }
 }
 
 // Arguments of the current window (args_i of simulation.py:591-596 and the t_span of
@@ -556,73 +410,6 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     // The top-boundary closure (bc_fun: (y[0], z = x[0])) rides along as one
     // extra cell of the last thread in the last round, where that thread has no
     // midpoint of its own (nx <= NT*CPT), so the closure code exists only once.
-    if constexpr (CPT >= HB_BATCH_MIN_CPT) {
-    // Narrow instances: the closures of HB_CLOSURE_BATCH "virtual rounds" at a time (closure_batch).
-    // Virtual round 0 is the boundary closure (thread NT-1 alone), virtual round v >= 1 is round
-    // v-1 of the midpoints -- so the boundary rides in the same batch as the unsaturated top of the
-    // column.  A batch without any unsaturated cell in the warp skips the transcendental code.
-    constexpr int B = HB_CLOSURE_BATCH, NVR = CPT + 1;
-#pragma unroll 1
-    for (int v0 = 0; v0 < NVR; v0 += B) {
-        double ym[B], dyn[B], dyd[B], dy[B], e[B], phi[B], km[B], cf[B];
-        bool any_unsat = false;
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const int v = v0 + b, k = tid + (v - 1) * NT;
-            ym[b] = psi_sat; dyn[b] = 0.0; dyd[b] = 1.0; e[b] = 0.0; phi[b] = 1.0; km[b] = 0.0; cf[b] = 0.0;
-            if (v == 0) {
-                if (tid == NT - 1) {
-                    ym[b] = y[0]; e[b] = nr[0];
-                    phi[b] = par[HB_P_PHI_TOP]; km[b] = par[HB_P_KMEAN_TOP]; cf[b] = par[HB_P_COEF_TOP];
-                }
-            } else if (v < NVR && k < nx - 1) {
-                const double y0 = y[k], y1 = y[k + 1];
-                ym[b] = 0.5 * (y0 + y1);
-                dyn[b] = y1 - y0; dyd[b] = c.dx[k];
-                e[b] = nr[k == 0 ? 0 : k - 1];          // noise index local to the closure's array (quirk Q1)
-                phi[b] = S.phi[k]; km[b] = S.km[k]; cf[b] = S.cf[k];
-            }
-            any_unsat |= !(ym[b] >= psi_sat);
-        }
-        div_batch<B>(dyn, dyd, dy);
-        Clos cl[B];
-        if (__any_sync(HB_FULL, any_unsat)) closure_batch<B>(par, ym, phi, km, cf, e, cl);
-        else {
-            const bool vg = par[HB_P_MODEL] != 0.0;
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-                cl[b].theta = phi[b]; cl[b].C = par[HB_P_EPS];
-                cl[b].kb = (!vg && cf[b] >= 0.0) ? km[b] : par[HB_P_KSAT_SOIL];
-                cl[b].K = cl[b].kb;
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const int v = v0 + b, k = tid + (v - 1) * NT;
-            bool unsat_interior = false;
-            if (v == 0) {
-                if (tid == NT - 1) {
-                    const double q_inf_max = fmin(2.0 * (phi[b] - cl[b].theta) * par[HB_P_DZ], cl[b].kb);
-                    double p_left = 0.0;
-                    if (ym[b] < psi_sat) p_left = fmin((1.0 - par[HB_P_INTERCEPT]) * fabs(wa[WA_PRECIP]), q_inf_max);
-                    if (mode == 1) p_left -= evaporation(par, ym[b]);
-                    HB_XA(c, NV, X_MISC)[0] = p_left;
-                }
-            } else if (v < NVR && k < nx - 1) {
-                cm[k] = cl[b].C;
-                double fl = cl[b].K * (dy[b] - 1.0);
-                if (hl_on) fl = hydraulic_lift(c, par, col, k, ym[b], dy[b], fl);
-                fm[k] = fl;
-                if (et_on) thm[k] = cl[b].theta;
-                unsat_interior = (k >= 1) && !(ym[b] >= psi_sat);
-            }
-            if (v >= 1 && v < NVR) {
-                const unsigned mask = __ballot_sync(HB_FULL, unsat_interior);
-                if (mask) deepest = max(deepest, (warp << 5) + (v - 1) * NT + (31 - __clz(mask)));
-            }
-        }
-    }
-    } else {
 #pragma unroll 1
     for (int r = 0; r < CPT * HB_DUP(c, 4); ++r) {
         const int k = tid + (r % CPT) * NT;
@@ -641,14 +428,7 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
                 e = nr[k == 0 ? 0 : k - 1];
                 phi = S.phi[k]; km = S.km[k]; cf = S.cf[k];
             }
-#if HB_CLOSURE_INLINE
-            Clos cl1[1];
-            { const double a1[1] = {ym}, a2[1] = {phi}, a3[1] = {km}, a4[1] = {cf}, a5[1] = {e};
-              closure_batch<1>(par, a1, a2, a3, a4, a5, cl1); }
-            const Clos cl = cl1[0];
-#else
             const Clos cl = closure(par, ym, phi, km, cf, e);
-#endif
             if (!bnd) {
                 cm[k] = cl.C;
                 double fl = cl.K * (dy - 1.0);
@@ -666,7 +446,6 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
         }
         const unsigned mask = __ballot_sync(HB_FULL, unsat_interior);
         if (mask) deepest = max(deepest, (warp << 5) + (r % CPT) * NT + (31 - __clz(mask)));
-    }
     }
     int *wmax = reinterpret_cast<int *>(HB_XA(c, NV, X_WMAX));
     if (lane == 0) wmax[warp] = deepest;
@@ -689,58 +468,42 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
     }
     double lat = 0.0;
     double *fo = HB_VEC(c, out);
-    // numerator and denominator of node i (the three node types of richards_pde.py:109-156):
-    //   top     (p_left + (f_0 + zx*s_0)) / (zx*C_0)
-    //   inner   (f_i - f_{i-1} + (zx*s_i + xz*s_{i-1})) / (zx*C_i + xz*C_{i-1})
-    //   bottom  (0 + (f_{n-2} - xz*s_{n-2})) / (-xz*C_{n-2})
-    auto node = [&](int i, double &num, double &den) {
-        const double yi = y[i];
-        // sink at midpoints i and i-1: root uptake (<= 0, daylight) and, inside
-        // the lateral-flow range, min(alpha_lat * psi_mid, sink)
-        double s_i = (et_on && i < nx - 1) ? sk[i] : 0.0, s_m = (et_on && i >= 1) ? sk[i - 1] : 0.0;
-        if (i >= lo && i < hi) {          // own midpoint i
-            s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), s_i);
-            lat += fabs(s_i);
-        }
-        if (i - 1 >= lo && i - 1 < hi)    // midpoint i-1
-            s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), s_m);
-        if (i == 0) {
-            const double zx = c.zx[0];
-            den = zx * cm[0];
-            num = HB_XA(c, NV, X_MISC)[0] + (fm[0] + zx * s_i);
-        } else if (i < nx - 1) {
-            const double zx = c.zx[i], xz = c.xz[i];
-            den = zx * cm[i] + xz * cm[i - 1];
-            num = fm[i] - fm[i - 1] + (zx * s_i + xz * s_m);
-        } else {
-            const double xz = c.xz[i];
-            den = -xz * cm[i - 1];
-            num = 0.0 + (fm[i - 1] - xz * s_m);
-        }
-        if (den == 0.0) den = 1.0;
-    };
-    if constexpr (CPT >= HB_BATCH_MIN_CPT) {
-        double num[CPT], den[CPT], qv[CPT];
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) {
-            const int i = tid + r * NT;
-            num[r] = 0.0; den[r] = 1.0;
-            if (i < nx) node(i, num[r], den[r]);
-        }
-        div_cells<CPT>(num, den, qv);
-#pragma unroll
-        for (int r = 0; r < CPT; ++r) if (const int i = tid + r * NT; i < nx) fo[i] = qv[r];
-    } else {
 #pragma unroll
     for (int r = 0; r < CPT * HB_DUP(c, 8); ++r) {
         const int i = tid + (r % CPT) * NT;
         if (HB_DUP_PROBE && r == CPT) lat = 0.0;
         if (i < nx) {
+            const double yi = y[i];
+            // sink at midpoints i and i-1: root uptake (<= 0, daylight) and, inside
+            // the lateral-flow range, min(alpha_lat * psi_mid, sink)
+            double s_i = (et_on && i < nx - 1) ? sk[i] : 0.0, s_m = (et_on && i >= 1) ? sk[i - 1] : 0.0;
+            if (i >= lo && i < hi) {          // own midpoint i
+                s_i = fmin(-2.5e-4 * (0.5 * (yi + y[i + 1])), s_i);
+                lat += fabs(s_i);
+            }
+            if (i - 1 >= lo && i - 1 < hi)    // midpoint i-1
+                s_m = fmin(-2.5e-4 * (0.5 * (y[i - 1] + yi)), s_m);
+            // the three node types of richards_pde.py:109-156:
+            //   top     (p_left + (f_0 + zx*s_0)) / (zx*C_0)
+            //   inner   (f_i - f_{i-1} + (zx*s_i + xz*s_{i-1})) / (zx*C_i + xz*C_{i-1})
+            //   bottom  (0 + (f_{n-2} - xz*s_{n-2})) / (-xz*C_{n-2})
             double num, den;
-            node(i, num, den);
+            if (i == 0) {
+                const double zx = c.zx[0];
+                den = zx * cm[0];
+                num = HB_XA(c, NV, X_MISC)[0] + (fm[0] + zx * s_i);
+            } else if (i < nx - 1) {
+                const double zx = c.zx[i], xz = c.xz[i];
+                den = zx * cm[i] + xz * cm[i - 1];
+                num = fm[i] - fm[i - 1] + (zx * s_i + xz * s_m);
+            } else {
+                const double xz = c.xz[i];
+                den = -xz * cm[i - 1];
+                num = 0.0 + (fm[i - 1] - xz * s_m);
+            }
+            if (den == 0.0) den = 1.0;
             fo[i] = hb_div(num, den);
         }
-    }
     }
     lat = warp_sum(lat);
     if (lane == 0) HB_XA(c, NV, X_LATW)[warp] = lat;
@@ -1127,7 +890,7 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
     const int q = order + 1;
     double *ru = HB_XA(c, NV, X_RU);
     __syncthreads();                       // previous readers of RU are done
-    for (int e_ = tid; e_ < q * q; e_ += NT) {     // (NT may be smaller than 36: narrow instances)
+    for (int e_ = tid; e_ < q * q; e_ += NT) {     // (NT may be smaller than 36: narrow A/B shapes)
         const int i = e_ / q, j = e_ % q;
         double acc = 0.0;
         for (int k = 0; k < q; ++k) {
@@ -1215,14 +978,8 @@ __device__ __forceinline__ void column_stats(const double *fb, const double *fn,
 // per-CTA global scratch is NOT used; X_PCR (dead while a Jacobian is built).
 // ---------------------------------------------------------------------------
 #define HB_JAC_MAXG 8
-#ifndef HB_JACF_BATCH
-#define HB_JACF_BATCH 0
-#endif
-#ifndef HB_JACF_ATTR
-#define HB_JACF_ATTR __noinline__
-#endif
 template <int NT, int CPT, bool FULL>
-__device__ HB_JACF_ATTR void jac_fused(const DevCtx &c, int col)
+__device__ __noinline__ void jac_fused(const DevCtx &c, int col)
 {
     constexpr int NV = FULL ? NVEC_FULL : NVEC_BASE;
     __syncthreads();                                 // the caller's parked controller state is visible
@@ -1266,21 +1023,6 @@ __device__ HB_JACF_ATTR void jac_fused(const DevCtx &c, int col)
             const double y0p = y0 + hv[k], y1p = y1 + hv[k + 1];
             const double e = nr[k == 0 ? 0 : k - 1];
             const double phi = S.phi[k], km = S.km[k], cf = S.cf[k], dxk = c.dx[k];
-#if HB_JACF_BATCH
-            {   // L (y[k] perturbed) and R (y[k+1] perturbed) as one batch of two independent chains
-                const double ymv[2] = {0.5 * (y0p + y1), 0.5 * (y0 + y1p)}, phv[2] = {phi, phi}, kmv[2] = {km, km},
-                             cfv[2] = {cf, cf}, ev[2] = {e, e};
-                const double dn[2] = {y1 - y0p, y1p - y0}, dd2[2] = {dxk, dxk};
-                double dyv[2];
-                div_batch<2>(dn, dd2, dyv);
-                Clos cl[2];
-                closure_batch<2>(par, ymv, phv, kmv, cfv, ev, cl);
-                double flL = cl[0].K * (dyv[0] - 1.0), flR = cl[1].K * (dyv[1] - 1.0);
-                if (hl_on) { flL = hydraulic_lift(c, par, col, k, ymv[0], dyv[0], flL); flR = hydraulic_lift(c, par, col, k, ymv[1], dyv[1], flR); }
-                cl_[k] = cl[0].C; fl_[k] = flL; cr[k] = cl[1].C; fr[k] = flR;
-                uL = (k >= 1) && !(ymv[0] >= psi_sat); uR = (k >= 1) && !(ymv[1] >= psi_sat);
-            }
-#else
             {   // L: y[k] perturbed
                 const double ym = 0.5 * (y0p + y1), dy = hb_div(y1 - y0p, dxk);
                 const Clos cl = closure(par, ym, phi, km, cf, e);
@@ -1297,7 +1039,6 @@ __device__ HB_JACF_ATTR void jac_fused(const DevCtx &c, int col)
                 cr[k] = cl.C; fr[k] = fl;
                 uR = (k >= 1) && !(ym >= psi_sat);
             }
-#endif
             u0 = (k >= 1) && !(0.5 * (y0 + y1) >= psi_sat);
             gk = c.grp[k]; gk1 = c.grp[k + 1];
         }
@@ -1579,21 +1320,6 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     for (int i = tid; i < nx; i += NT) { const double dy = b[i]; const double q = hb_div(dy, vscl[i]); loc += q * q; s1[i] = y[i] + dy; s2[i] = vd[i] + dy; }
                     loc = 0.0; }
 #endif
-                if constexpr (CPT >= HB_BATCH_MIN_CPT) {
-                    double dyv[CPT], scv[CPT], qv[CPT];
-#pragma unroll
-                    for (int r_ = 0; r_ < CPT; ++r_) {
-                        const int i = tid + r_ * NT;
-                        dyv[r_] = 0.0; scv[r_] = 1.0;
-                        if (i < nx) { dyv[r_] = tri_x<NV, FULL>(c, i); scv[r_] = vscl[i]; }
-                    }
-                    div_cells<CPT>(dyv, scv, qv);
-                    HB_FOR_CELLS(i) {
-                        loc += qv[r_] * qv[r_];
-                        y[i] += dyv[r_];               // tentative: discarded if we stop
-                        vd[i] += dyv[r_];
-                    }
-                } else
                 HB_FOR_CELLS(i) {
                     const double dy = tri_x<NV, FULL>(c, i);
                     const double q = hb_div(dy, vscl[i]);
@@ -1645,21 +1371,6 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                 const double safety = 0.9 * (2 * HB_NEWTON_MAXITER + 1) /
                                       (double)(2 * HB_NEWTON_MAXITER + n_iter);
                 double le = 0.0;
-                if constexpr (CPT >= HB_BATCH_MIN_CPT) {
-                    double nv[CPT], scv[CPT], qv[CPT];
-#pragma unroll
-                    for (int r_ = 0; r_ < CPT; ++r_) {
-                        const int i = tid + r_ * NT;
-                        nv[r_] = 0.0; scv[r_] = 1.0;
-                        if (i < nx) {
-                            scv[r_] = atol + rtol * fabs(y[i]);
-                            vscl[i] = scv[r_];
-                            nv[r_] = k_error_const[order] * vd[i];
-                        }
-                    }
-                    div_cells<CPT>(nv, scv, qv);
-                    HB_FOR_CELLS(i) le += qv[r_] * qv[r_];
-                } else
                 for (int rp_ = 0; rp_ < HB_DUP(c, 512); ++rp_) { le = 0.0;
                 HB_FOR_CELLS(i) {
                     const double sc = atol + rtol * fabs(y[i]);
@@ -1697,39 +1408,6 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
                     if (c.dbg & 2048) change_D<NT, CPT, NV>(c, order, 1.0);
 #endif
                     double lm = 0.0, lp = 0.0;
-                    if constexpr (CPT >= HB_BATCH_MIN_CPT) {
-                        // (the rows of the table in the outer loop, the thread's cells unrolled inside:
-                        // the loads of a row are independent of one another)
-                        double nm[CPT], np_[CPT], scv[CPT], qm[CPT], qp[CPT], acc[CPT];
-#pragma unroll
-                        for (int r_ = 0; r_ < CPT; ++r_) {
-                            const int i = tid + r_ * NT;
-                            nm[r_] = 0.0; np_[r_] = 0.0; scv[r_] = 1.0; acc[r_] = 0.0;
-                            if (i < nx) {
-                                const double di = vd[i];
-                                const double dlast = di - D[(order + 1) * nxp + i];
-                                D[(order + 2) * nxp + i] = dlast;
-                                D[(order + 1) * nxp + i] = di;
-                                acc[r_] = di;
-                                np_[r_] = k_error_const[order < HB_MAX_ORDER ? order + 1 : 0] * dlast;
-                                scv[r_] = vscl[i];
-                            }
-                        }
-                        for (int kk = order; kk >= 0; --kk) {
-                            HB_FOR_CELLS(i) {
-                                acc[r_] = D[kk * nxp + i] + acc[r_];
-                                D[kk * nxp + i] = acc[r_];
-                            }
-                            if (kk == order) {
-#pragma unroll
-                                for (int r_ = 0; r_ < CPT; ++r_) nm[r_] = k_error_const[order > 1 ? order - 1 : 0] * acc[r_];
-                            }
-                        }
-                        if (decide) {
-                            if (order > 1) { div_cells<CPT>(nm, scv, qm); HB_FOR_CELLS(i) lm += qm[r_] * qm[r_]; }
-                            if (order < HB_MAX_ORDER) { div_cells<CPT>(np_, scv, qp); HB_FOR_CELLS(i) lp += qp[r_] * qp[r_]; }
-                        }
-                    } else
                     HB_FOR_CELLS(i) {
                         const double di = vd[i];
                         D[(order + 2) * nxp + i] = di - D[(order + 1) * nxp + i];
@@ -1973,29 +1651,6 @@ behind_eval:
             // ---- predictor, scale, psi (bdf.py:360-366) ----------------------
             cc = hb_div(t_new - t, k_alpha[order]);
             __syncthreads();
-            if constexpr (CPT >= HB_BATCH_MIN_CPT) {
-                double psv[CPT], alv[CPT], qv[CPT], acc[CPT];
-#pragma unroll
-                for (int r_ = 0; r_ < CPT; ++r_) {
-                    const int i = tid + r_ * NT;
-                    psv[r_] = 0.0; alv[r_] = k_alpha[order];
-                    acc[r_] = (i < nx) ? D[i] : 0.0;
-                }
-                for (int kk = 1; kk <= order; ++kk) {
-                    const double gk = k_gamma[kk];
-                    HB_FOR_CELLS(i) {
-                        const double dk = D[kk * nxp + i];
-                        acc[r_] += dk; psv[r_] += dk * gk;
-                    }
-                }
-                div_cells<CPT>(psv, alv, qv);
-                HB_FOR_CELLS(i) {
-                    y[i] = acc[r_];
-                    vscl[i] = atol + rtol * fabs(acc[r_]);
-                    vd[i] = 0.0;
-                    vpsi[i] = qv[r_];
-                }
-            } else
             for (int rp_ = 0; rp_ < HB_DUP(c, 32); ++rp_)
             HB_FOR_CELLS(i) {
                 double acc = D[i], ps = 0.0;

@@ -9,6 +9,7 @@ GPU tests added in round 2 (run on the B200 box, all through the C-ABI):
   vectors, the Philox stream (moments, KS, stream disjointness);
 * failed attempts under time-sliced scheduling (the damped base noise field is
   handed from SM to SM) are schedule independent;
+* the one-pass Jacobian differences (jac_fused) are bit-identical to the evaluation per group;
 * a noise tape that is too short fails loudly;
 * per-column forcing series, ensemble statistics incl. theta moments, the
   multi-GPU entry `EnsembleSimulation.from_global`, the command-line entry point.
@@ -291,6 +292,112 @@ def test_failed_attempts_are_schedule_independent():
         assert np.mean(o_wscal[:, pack.W_STATUS] == status[c]) >= 0.9, c
         assert abs(int(o_stats[pack.C_NFAIL]) - int(fails[c])) <= 5, c
         assert abs(o_wscal[-1, pack.W_WTD_EST] - ref[1][c, -1, pack.W_WTD_EST]) <= 1, c
+
+
+def _both_jacobian_paths(work):
+    """Run `work()` with the grouped Jacobian differences made in one pass (the default,
+    jac_fused) and with one right-hand-side evaluation per colour group (HB_JAC_SEQ=1, scipy's own
+    sequence of evaluations); returns the two result tuples."""
+    res = []
+    for seq in (False, True):
+        os.environ.pop("HB_JAC_SEQ", None)
+        if seq:
+            os.environ["HB_JAC_SEQ"] = "1"
+        try:
+            res.append(work())
+        finally:
+            os.environ.pop("HB_JAC_SEQ", None)
+    return res
+
+
+def test_fused_jacobian_is_bit_identical():
+    """num_jac's first pass over the colour groups (SCIPY common.py:385-443) is made in ONE pass on
+    the device: two closure evaluations per midpoint (own node perturbed / right neighbour
+    perturbed) instead of one whole right-hand-side evaluation per group, the three rows of every
+    column assembled from them.  Every number must be the one the evaluation per group produces:
+    states, per-row scalars, output fields and all solver counters are compared bit for bit over
+    (1) a mixed ensemble (both closures, all porosity profiles, lateral-flow sink on) with daily
+    rows, (2) the same without the lateral-flow sink, (3) half-hourly rows with hydraulic lift at
+    night (fused) and the root-uptake sink by day (evaluation per group), (4) failed attempts with
+    the damped noise field, (5) the spin-up kernel, (6) the default column (n = 2 closure)."""
+    n_cols, T = 192, 31
+    table = synthetic_forcing(365).iloc[:T].reset_index(drop=True)
+    base, cols = ensemble_columns(default_params(SITE), 4096, n_cols, mixed=True, perturb_theta=True)
+    ens = pack.pack_ensemble(base, table, cols)
+    ic = np.tile(np.load(IC), (n_cols, 1))
+
+    def run(e, rows, tape=None, stride=10):
+        ctx, _ = open_ctx(e)
+        if tape is None:
+            ctx.set_noise_philox(SEED, 4096)
+        else:
+            ctx.set_noise_tape(tape)
+        ctx.set_output(stride)
+        ctx.set_state(ic[:e["par"].shape[0]])
+        ctx.reset_counters()
+        ctx.run(0, rows)
+        out = (ctx.get_state(), ctx.get_wscal(), ctx.get_fields(), ctx.get_counters())
+        ctx.close()
+        return out
+
+    def same(a, b, what):
+        for u, v, name in zip(a, b, ("state", "per-row scalars", "fields", "counters")):
+            assert np.array_equal(u, v, equal_nan=True), (what, name)
+
+    # (1) mixed ensemble, default flags (LF on; ET flag set but daily rows are night rows)
+    a, b = _both_jacobian_paths(lambda: run(ens, T))
+    same(a, b, "mixed ensemble")
+    njev = a[3][:, pack.C_NJEV].sum() / a[3][:, pack.C_NWINDOWS].sum()
+    assert njev > 1.2, "the workload must build Jacobians"
+    # (2) no lateral-flow sink
+    e2 = dict(ens); e2["par"] = ens["par"].copy(); e2["par"][:, pack.P_FLAGS] = 0.0
+    a2, b2 = _both_jacobian_paths(lambda: run(e2, T))
+    same(a2, b2, "no sinks")
+    assert not np.array_equal(a[0], a2[0])
+    # (3) half-hourly rows, hydraulic lift + root uptake (gentle demand keeps the daylight rows cheap)
+    hh = synthetic_forcing(40, half_hourly=True)
+    e3 = pack.pack_ensemble(base, hh, {k: v[:48] for k, v in cols.items()})
+    e3["par"] = e3["par"].copy(); e3["par"][:, pack.P_FLAGS] = 7.0          # LF | ET | HLIFT
+    e3["forcing"] = dict(e3["forcing"]); e3["forcing"]["atm"] = e3["forcing"]["atm"] * 1.0e-3
+    assert e3["forcing"]["daylight"].any() and not e3["forcing"]["daylight"].all()
+    a3, b3 = _both_jacobian_paths(lambda: run(e3, 40, stride=8))
+    same(a3, b3, "half-hourly, HLIFT + ET")
+    # (4) failed attempts (noise field damped in place, attempts restarted)
+    e4 = {k: (v[:64] if k in ("par", "stat") else v) for k, v in ens.items()}
+    f = ens["forcing"]
+    rows = np.arange(T)
+    slots = 1 + int((((f["precipitation_cm"] > 0.5) | (rows % 48 == 0)) & (rows > 0)).sum())
+    tape = np.random.default_rng(78).standard_normal((64, slots, 401))
+    tape[:, 0] *= 1.0e6
+    a4, b4 = _both_jacobian_paths(lambda: run(e4, 20, tape=tape))
+    same(a4, b4, "failed attempts")
+    assert (a4[3][:, pack.C_NFAIL] >= 5).sum() >= 16       # (van Genuchten members ignore the noise field)
+    # (5) spin-up kernel, (6) default column (n == 2 closure) in the window loop
+    col = default_column()
+
+    def spin():
+        ctx = capi.Context(401, 8)
+        grp, ng = pack.fd_groups(401)
+        ctx.set_grid(col["x"], grp, ng)
+        ctx.set_columns(np.tile(col["par"], (8, 1)), np.tile(col["stat"], (8, 1, 1)))
+        fc = col["forcing"]
+        ctx.set_forcing(fc["precipitation_cm"][:25], fc["wtd_idx"][:25], fc["daylight"][:25], fc["atm"][:25])
+        ctx.set_noise_philox(SEED, 0)
+        psi0 = np.tile(np.load(IC), (8, 1)) * np.linspace(0.9, 1.1, 8)[:, None]
+        ctx.set_state(psi0)
+        iters = ctx.spinup(fc["zWtd_cm"][0], None, max_iter=25)
+        spun = ctx.get_state()
+        ctx.set_output(6)
+        ctx.reset_counters()
+        ctx.run(0, 25)
+        out = (spun, ctx.get_wscal(), ctx.get_fields(), ctx.get_counters(), iters, ctx.get_state())
+        ctx.close()
+        return out
+
+    a5, b5 = _both_jacobian_paths(spin)
+    for u, v in zip(a5, b5):
+        assert np.array_equal(u, v, equal_nan=True)
+    assert col["par"][pack.P_N] == 2.0
 
 
 def test_short_noise_tape_fails_loudly():
