@@ -64,12 +64,14 @@ def log(*a):
 NCU_TRAFFIC = {
     (1, 1024, 365, 30): {"bytes": 352691712 + 269521152,
                          "source": "profiles/ncu_r01_bench_run_kernel_summary.txt"},
-    # round 2, automatic chunk length (65,536 columns: one 120-row chunk per column and launch;
-    # with round 1's fixed 16-row chunks the same launch moved 9.27 + 2.66 GB, profiles/launches_r02.csv)
-    (2, 65536, 120, 365): {"bytes": 1690220544 + 1282057472,
-                           "source": "profiles/traffic_r02_cfg2_65536.csv"},
-    (2, 8192, 120, 365): {"bytes": 617554432 + 201320448,
-                          "source": "profiles/traffic_r02_cfg2_8192.csv"},
+    # round 2, final kernel (fused Jacobian pass, automatic chunk length: one 120-row chunk per column
+    # and launch): mean of the two captured launches, 1.40 + 0.79 GB (rows 121-240) and 1.61 + 1.09 GB
+    # (rows 241-360); before the fused pass the same launches moved 2.97 GB, with round 1's fixed
+    # 16-row chunks 9.27 + 2.66 GB (profiles/launches_r02.csv)
+    (2, 65536, 120, 365): {"bytes": (1399839744 + 794851072 + 1611140352 + 1088582912) // 2,
+                           "source": "profiles/traffic_r02b_cfg2_65536.csv"},
+    (2, 8192, 120, 365): {"bytes": 607025152 + 205332992,
+                          "source": "profiles/ncu_r02b_cfg2_run_kernel_summary.txt"},
 }
 
 
@@ -606,6 +608,13 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     own_launch_s = float(np.sum(kernel_ms)) * 1e-3 / a.steps    # this rank's launches
     ach_tf = flops / own_launch_s / 1e12
+    # The device makes the grouped differences of a Jacobian (one right-hand-side evaluation per colour
+    # group in scipy, counted as such in C_NRHS) in one pass of two closure evaluations per midpoint:
+    # `frac_executed` charges such a Jacobian 2 evaluations instead of n_groups.
+    n_groups = int(pack.fd_groups(nx)[1])
+    c_exec = counters.astype(float).copy()
+    c_exec[:, pack.C_NRHS] -= c_exec[:, pack.C_NJEV] * (n_groups - 2)
+    ach_tf_exec = algorithmic_flops(c_exec, nx) / counted_steps / own_launch_s / 1e12
     tr = NCU_TRAFFIC.get((a.config, n_cols, rps, out_stride))
     ach_gbs = abytes / own_launch_s / 1e9
     csum = counters.sum(axis=0).astype(float)
@@ -629,14 +638,18 @@ def main():
         "slowest_step_ms_this_rank": float(np.max(kernel_ms)), "median_step_ms_this_rank": float(np.median(kernel_ms)),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_fp64, "unit": "TFLOP/s",
-                     "frac": ach_tf / peak_fp64, "traffic": tr["bytes"] if tr else None,
+                     "frac": ach_tf / peak_fp64, "frac_executed": ach_tf_exec / peak_fp64,
+                     "traffic": tr["bytes"] if tr else None,
                      "traffic_unit": "DRAM bytes per launch (read + write)",
                      "traffic_source": tr["source"] if tr else None,
                      "peak_source": "hb_measure_fp64_peak: register-resident DFMA loop measured in "
                                     "this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "flops_per_launch": flops, "kernel": "run_kernel<256,2,2,true>",
-                     "note": "algorithmic FP64 flop of SURVEY 8(d) from the kernel's own counters; "
-                             "the path is an SMEM-resident FP64 solver, neither HBM- nor tensor-bound"},
+                     "note": "algorithmic FP64 flop of SURVEY 8(d) from the kernel's own counters (the "
+                             "evaluations the reference's algorithm makes); frac_executed counts a Jacobian's "
+                             "grouped differences as the 2 evaluations the fused pass costs instead of one per "
+                             "colour group; the path is an SMEM-resident FP64 solver, neither HBM- nor "
+                             "tensor-bound"},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "bytes_per_launch": abytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},

@@ -1209,9 +1209,10 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     bool lu_valid = false, current_jac = false, have_old = false, jac_first = true, jac_init = true;
     bool any_accept = false;                        // a step of THIS attempt has been accepted
     // grouped forward differences of the Jacobian in one pass (jac_fused) unless the root-uptake
-    // sink is active in this window (its global sums need the evaluation per group)
+    // sink is active in this window (its global sums need the evaluation per group); the fast-mode
+    // instance keeps its three evaluations (measured: the pass saves little there and costs spills)
     // (recomputed where it is needed: nothing of it stays live across the integrator loop)
-#define HB_JAC_FUSE(c, NV, wa) ((c).jac_fuse && !((int)(wa)[WA_MODE] == 1 && ((int)HB_XA(c, NV, X_PAR)[HB_P_FLAGS] & HB_FLAG_ET)))
+#define HB_JAC_FUSE(c, NV, wa) (!FAST && (c).jac_fuse && !((int)(wa)[WA_MODE] == 1 && ((int)HB_XA(c, NV, X_PAR)[HB_P_FLAGS] & HB_FLAG_ET)))
     double t = wa[WA_T0], t_new = t, h_abs = 0.0, h_loc = 0.0, min_step = 0.0, cc = 0.0, c_lu = 0.0;
     double dy_norm_old = 0.0, d1_init = 0.0, h0_init = 0.0;
 
@@ -1220,7 +1221,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     int go = GO_NONE;
     bool jb_now = false;
     __syncthreads();
-    if (after_jac) {
+    if (!FAST && after_jac) {
         // ---- back from jac_fused: the differences of all first-pass groups are in place -----------
         t = ctl[0]; t_new = ctl[1]; h_abs = ctl[2]; h_loc = ctl[3]; min_step = ctl[4]; cc = ctl[5];
         c_lu = ctl[6]; dy_norm_old = ctl[7]; d1_init = ctl[8]; h0_init = ctl[9];
@@ -1230,11 +1231,9 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         // what the S_JG branch does after its last group: the retry pass over the groups that hold a
         // column whose difference was too small (10x step), one evaluation per group
         int want = c.ng;
-        if (!FAST) {                                    // (fast mode has no retry pass)
-            for (int j = tid; j < nx; j += NT)
-                if (vd[j] != 0.0) want = min(want, c.grp[j]);
-            want = -block_max_int<NT, NV>(c, par_, -want);
-        }
+        for (int j = tid; j < nx; j += NT)
+            if (vd[j] != 0.0) want = min(want, c.grp[j]);
+        want = -block_max_int<NT, NV>(c, par_, -want);
         state = S_JG;
         if (want >= c.ng) go = GO_JAC_END;
         else {
@@ -1267,7 +1266,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
     }
 
     // (re-entry after jac_fused: into the loop behind the evaluation, with `go` as set above)
-    if (after_jac) goto behind_eval;
+    if (!FAST && after_jac) goto behind_eval;
     for (;;) {
         go = GO_NONE;
         jb_now = false;
