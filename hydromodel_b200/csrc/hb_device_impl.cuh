@@ -971,11 +971,16 @@ __device__ __forceinline__ void column_stats(const double *fb, const double *fn,
 // root-water-uptake sink (daylight, ET on: global sums over the profile) keep the
 // evaluation per group, and so does the retry pass with the 10x steps.
 //
-// In:  V_TVL base point, V_TVR steps h, V_TW f(base), cm0 / fm0 = C and flux of the base
-//      evaluation at the midpoints, p_left0 its boundary flux.
-// Out: V_JL/V_JD/V_JU, V_PSI, V_SCL, V_DD exactly as the S_JG state leaves them.
-// Scratch: V_Y (C of L), V_B (flux of L), V_TIP (C of R), G_FAC untouched, one row of the
-// per-CTA global scratch is NOT used; X_PCR (dead while a Jacobian is built).
+// In:  V_TVL base point, V_TVR steps h, V_TW f(base); C, flux and boundary flux of the base
+//      evaluation: V_CM / V_FM / MISC[0] when the S_JB state has just made it, else (initial
+//      Jacobian) the copies the S_F0 state left in the scratch rows G_TH / G_SK and MISC[2]
+//      (free: the root-uptake sink is off in every window that comes here); which of the two
+//      is flagged in the parked controller state (X_RU).
+// Out: V_JL/V_JD/V_JU, V_PSI, V_SCL, V_DD exactly as the S_JG state leaves them after its last group.
+// Scratch (all dead while a Jacobian is built): V_Y / V_B = C / flux of the L variants,
+//      V_TIP / V_DD = C / flux of the R variants (V_DD until the statistics overwrite it),
+//      V_JL/V_JD/V_JU = the three rows of f(y + h_g) per column before they become differences,
+//      X_PCR = per-group water-table reduction, f(y + h_g)[0] per group, perturbed boundary flux.
 // ---------------------------------------------------------------------------
 #define HB_JAC_MAXG 8
 template <int NT, int CPT, bool FULL>
@@ -990,7 +995,7 @@ __device__ __noinline__ void jac_fused(const DevCtx &c, int col)
     const double *fm0 = initial ? HB_GROW(c, G_SK) : HB_VEC(c, V_FM);
     const double p_left0 = HB_XA(c, NV, X_MISC)[initial ? 2 : 0];
     double *fr = HB_VEC(c, V_DD);
-    const Statics S = statics_of<FULL>(c, col);      // (by value here: a reference would pin the caller's copy in local memory)
+    const Statics S = statics_of<FULL>(c, col);
     const int nx = c.nx, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ng = c.ng;
     constexpr int NW = NT / 32;
     const double *wa = HB_XA(c, NV, X_ARGS);
