@@ -431,8 +431,9 @@ def main():
     if a.no_adaptive:
         ctx.set_schedule(False)
     if a.fast:
-        ctx.set_fast_mode(cont=True, jac3=True)
-        config["mode"] = "FAST (hb_set_fast_mode: warm-started windows, 3-colour FD Jacobian) -- not parity mode"
+        ctx.set_fast_mode(cont=True, jac3=True, f32=True)
+        config["mode"] = ("FAST (hb_set_fast_mode: warm-started windows, 3-colour FD Jacobian, single-precision "
+                          "closure inside the Newton iteration) -- not parity mode")
 
     def upload():
         """Host -> device copies of one step: statics, forcing, (tape), state."""

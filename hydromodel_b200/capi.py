@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 from .pack import NPARAM, NSTATIC, NWSCAL, NFIELD, NCOUNTER
 
-FAST_CONT, FAST_JAC3 = 1, 2          # include/hb_layout.h HB_FAST_*
+FAST_CONT, FAST_JAC3, FAST_F32 = 1, 2, 4          # include/hb_layout.h HB_FAST_*
 
 _lib = None
 
@@ -244,9 +244,10 @@ class Context:
     def run(self, w0=0, w1=None):
         self._ck(self.lib.hb_run(self._h, int(w0), int(self.T if w1 is None else w1)))
 
-    def set_fast_mode(self, cont=True, jac3=True):
+    def set_fast_mode(self, cont=True, jac3=True, f32=False):
         """Fast mode of ``run`` (never the default): see HB_FAST_* in include/hb_layout.h."""
-        self._ck(self.lib.hb_set_fast_mode(self._h, (FAST_CONT if cont else 0) | (FAST_JAC3 if jac3 else 0)))
+        self._ck(self.lib.hb_set_fast_mode(self._h, (FAST_CONT if cont else 0) | (FAST_JAC3 if jac3 else 0) |
+                                           (FAST_F32 if f32 else 0)))
 
     def set_schedule(self, adaptive=True):
         self._ck(self.lib.hb_set_schedule(self._h, int(bool(adaptive))))

@@ -837,7 +837,7 @@ int hb_reset_counters(hb_ctx *ctx)
 int hb_set_fast_mode(hb_ctx *ctx, int flags)
 {
     if (!ctx) return fail("null ctx");
-    if (flags & ~(HB_FAST_CONT | HB_FAST_JAC3)) return fail("hb_set_fast_mode: unknown flag");
+    if (flags & ~(HB_FAST_CONT | HB_FAST_JAC3 | HB_FAST_F32)) return fail("hb_set_fast_mode: unknown flag");
     ctx->fast_flags = flags;
     return 0;
 }

@@ -140,6 +140,43 @@ __device__ __forceinline__ Clos closure(const double *par, double psi, double ph
     return r;
 }
 
+// Fast mode only (HB_FAST_F32, never the default): the same map in single precision with the
+// hardware exp2 / log2, for the evaluations inside the Newton iteration.  1 - Se and the noise
+// term's log(1 + x) use expm1 / log1p so that nothing cancels at float precision near saturation.
+// Saturated cells and the column-uniform rare cases are left to the double-precision code
+// (returns false).
+__device__ __forceinline__ bool closure_f32(const double *par, double psi_d, double phi_d, double kmean_d,
+                                            double coef_d, double e_d, Clos *out)
+{
+    const bool vg = par[HB_P_MODEL] != 0.0;
+    const double lam_d = par[HB_P_LAMBDA];
+    if (psi_d >= par[HB_P_PSI_SAT] || vg || (lam_d != 1.0 && lam_d != 2.0)) return false;
+    const float n = (float)par[HB_P_N], m = (float)par[HB_P_M], alpha = (float)par[HB_P_ALPHA];
+    const float th_r = (float)par[HB_P_THETA_RES];
+    const float delta_s = (float)phi_d - th_r;
+    const float ax = alpha * fabsf((float)psi_d);
+    const float xn = __expf(n * __logf(ax));
+    const float base = 1.0f + xn;
+    const float t = -m * log1pf(xn);
+    const float X = __expf(t);
+    const float one_minus_X = -expm1f(t);
+    const float s_eff = fminf(fmaxf(X, 0.0f), 1.0f);
+    float kb = (float)par[HB_P_KSAT_SOIL];
+    if (coef_d >= 0.0) {
+        const float mean = (kmean_d == 0.0) ? 1.0e-7f : (float)kmean_d;
+        const float var = (float)par[HB_P_SIGMA] * fminf(fmaxf(one_minus_X, 0.0f), 1.0f);
+        const float l1 = log1pf(var / (mean * mean));
+        kb = mean * __expf(-0.5f * l1 + sqrtf(l1) * ((float)coef_d * (float)e_d));
+    }
+    float K = ((lam_d == 1.0) ? s_eff : s_eff * s_eff) * kb;
+    K = fminf(K, kb);
+    float C = (m * n) * alpha * delta_s * (s_eff / base) * (xn / ax);
+    const float eps = (float)par[HB_P_EPS];
+    if (C < eps || !isfinite(C)) C = eps;
+    out->theta = (double)(th_r + delta_s * X); out->K = (double)K; out->C = (double)C; out->kb = (double)kb;
+    return true;
+}
+
 // Out-of-line copy for the diagnostics on the nodes (cold).
 __device__ __noinline__ void closure_cold(const double *par, double psi, double phi, double kmean,
                                           double coef, double e, Clos *out)
@@ -389,8 +426,9 @@ __device__ __noinline__ double evaporation(const double *par, double y0)
 // synchronises before the call).  The result is written to vector `out`
 // (each thread writes, and may afterwards read, its own cells).  Contains one
 // __syncthreads(); writes V_CM, V_FM and the small slots WMAX, MISC, LATW.
-template <int NT, int CPT, int NV>
-__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int col, int out, int &parity)
+template <int NT, int CPT, int NV, bool FAST = false>
+__device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int col, int out, int &parity,
+                                         bool f32 = false)
 {
     // the row's arguments (precipitation, demand, water-table observation, mode) are read from
     // shared memory where they are needed instead of living in registers across the integrator loop
@@ -428,7 +466,10 @@ __device__ __forceinline__ void rhs_eval(const DevCtx &c, const Statics &S, int 
                 e = nr[k == 0 ? 0 : k - 1];
                 phi = S.phi[k]; km = S.km[k]; cf = S.cf[k];
             }
-            const Clos cl = closure(par, ym, phi, km, cf, e);
+            Clos cl;
+            bool have = false;
+            if (FAST && f32) have = closure_f32(par, ym, phi, km, cf, e, &cl);      // (fast mode, Newton evaluations only)
+            if (!have) cl = closure(par, ym, phi, km, cf, e);
             if (!bnd) {
                 cm[k] = cl.C;
                 double fl = cl.K * (dy - 1.0);
@@ -1284,7 +1325,7 @@ __device__ __noinline__ int bdf_attempt(const DevCtx &c, int col,
         if (c.dbg & 8192) { __syncthreads(); __syncthreads(); }
 #endif
         HB_TICK(c, NV, 0);                   // controller glue since the last mark + loop-top barrier
-        rhs_eval<NT, CPT, NV>(c, S, col, out, par_);
+        rhs_eval<NT, CPT, NV, FAST>(c, S, col, out, par_, FAST && state == S_NW && (c.fast & HB_FAST_F32));
         HB_TICK(c, NV, 2);                   // assembly phase
         if (tid == 0) { cnt[K_NRHS]++; if (state == S_F0 || state == S_F1 || state == S_NW) cnt[K_NFEV]++; }
 

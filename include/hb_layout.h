@@ -103,7 +103,7 @@ enum {                       /* output field ids for hb_get_field           */
 
 /* Fast mode (hb_set_fast_mode; never the default -- results then differ from the
  * reference's arithmetic within the integrator's own tolerance).
- * Either flag selects the fast build of the window loop. */
+ * Any flag selects the fast build of the window loop. */
 #define HB_FAST_CONT     1   /* a window whose forcing row (precipitation, day/night, demand -- the
                               * water-table observation may differ) and noise field equal the previous window's is
                               * integrated as the CONTINUATION of that window: order, step size,
@@ -114,6 +114,12 @@ enum {                       /* output field ids for hb_get_field           */
 #define HB_FAST_JAC3     2   /* finite-difference Jacobian with the 3 colours j mod 3 instead of
                               * scipy's 5 groups, and without the 10x-step retry pass
                               * (common.py:268-455, _numdiff.py:227-284) */
+#define HB_FAST_F32      4   /* the closure of the right-hand-side evaluations INSIDE the Newton iteration
+                              * (bdf.py:41-67; 38 of the 46 evaluations of a window) in single precision
+                              * with the hardware exp2 / log2: theta, K, C carry a relative error of ~1e-6,
+                              * far below the Newton tolerance of 0.03 in units of atol + rtol |psi|.  The
+                              * evaluations that feed differences (select_initial_step, the finite-difference
+                              * Jacobian) stay in double precision (vrettas_fung.py:108-249) */
 
 /* integrator constants, scipy/integrate/_ivp/bdf.py:12-15,244-247 */
 #define HB_MAX_ORDER       5

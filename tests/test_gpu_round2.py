@@ -622,10 +622,10 @@ def test_fast_mode_against_parity_mode():
     ens = pack.pack_ensemble(base, table, cols)
     ic = np.load(IC)
     res = {}
-    for mode in ("parity", "fast"):
+    for mode in ("parity", "fast", "fast_f32"):
         ctx, _ = open_ctx(ens)
-        if mode == "fast":
-            ctx.set_fast_mode(cont=True, jac3=True)
+        if mode != "parity":
+            ctx.set_fast_mode(cont=True, jac3=True, f32=(mode == "fast_f32"))
         ctx.set_noise_philox(SEED, 0)
         ctx.set_output(20)
         ctx.set_state(np.tile(ic, (C, 1)))
@@ -633,18 +633,23 @@ def test_fast_mode_against_parity_mode():
         ctx.run(0, T)
         res[mode] = (ctx.get_state(), ctx.get_wscal(), ctx.get_fields(), ctx.get_counters())
         ctx.close()
-    (p_psi, p_ws, p_f, p_cn), (f_psi, f_ws, f_f, f_cn) = res["parity"], res["fast"]
-    d = np.abs(p_ws[:, :, pack.W_WTD_EST] - f_ws[:, :, pack.W_WTD_EST])
-    psi_units = np.max(np.abs(f_psi - p_psi) / (1e-3 + 1e-3 * np.abs(p_psi)), axis=1)
-    th_rel = np.max(np.abs(f_f[:, :, pack.F_THETA] - p_f[:, :, pack.F_THETA]) / p_f[:, :, pack.F_THETA])
-    rhs_ratio = f_cn[:, pack.C_NRHS].sum() / p_cn[:, pack.C_NRHS].sum()
-    print("fast vs parity: wtd node identical %.4f (max diff %d), psi units median %.3f max %.3f, theta rel max "
-          "%.2e, RHS evaluations x%.3f, steps x%.3f, Jacobians x%.3f, failed attempts %d vs %d" %
-          (np.mean(d == 0), d.max(), np.median(psi_units), psi_units.max(), th_rel, rhs_ratio,
-           f_cn[:, pack.C_NSTEPS].sum() / p_cn[:, pack.C_NSTEPS].sum(),
-           f_cn[:, pack.C_NJEV].sum() / p_cn[:, pack.C_NJEV].sum(), f_cn[:, pack.C_NFAIL].sum(), p_cn[:, pack.C_NFAIL].sum()))
-    assert np.all(f_ws[:, 1:, pack.W_STATUS] == 0)
-    assert d.max() <= 1 and np.mean(d == 0) >= 0.97
-    assert np.median(psi_units) < 30.0
-    assert th_rel < 3e-3
-    assert rhs_ratio < 0.9
+    p_psi, p_ws, p_f, p_cn = res["parity"]
+    for mode in ("fast", "fast_f32"):
+        # HB_FAST_F32 on top: the closure of the Newton evaluations in single precision (errors of
+        # ~1e-6 in theta, K, C against a Newton tolerance of 0.03 solver units) -- same bars
+        f_psi, f_ws, f_f, f_cn = res[mode]
+        d = np.abs(p_ws[:, :, pack.W_WTD_EST] - f_ws[:, :, pack.W_WTD_EST])
+        psi_units = np.max(np.abs(f_psi - p_psi) / (1e-3 + 1e-3 * np.abs(p_psi)), axis=1)
+        th_rel = np.max(np.abs(f_f[:, :, pack.F_THETA] - p_f[:, :, pack.F_THETA]) / p_f[:, :, pack.F_THETA])
+        rhs_ratio = f_cn[:, pack.C_NRHS].sum() / p_cn[:, pack.C_NRHS].sum()
+        print("%s vs parity: wtd node identical %.4f (max diff %d), psi units median %.3f max %.3f, theta rel max "
+              "%.2e, RHS evaluations x%.3f, steps x%.3f, Jacobians x%.3f, failed attempts %d vs %d" %
+              (mode, np.mean(d == 0), d.max(), np.median(psi_units), psi_units.max(), th_rel, rhs_ratio,
+               f_cn[:, pack.C_NSTEPS].sum() / p_cn[:, pack.C_NSTEPS].sum(),
+               f_cn[:, pack.C_NJEV].sum() / p_cn[:, pack.C_NJEV].sum(), f_cn[:, pack.C_NFAIL].sum(),
+               p_cn[:, pack.C_NFAIL].sum()))
+        assert np.all(f_ws[:, 1:, pack.W_STATUS] == 0), mode
+        assert d.max() <= 1 and np.mean(d == 0) >= 0.97, mode
+        assert np.median(psi_units) < 30.0, mode
+        assert th_rel < 3e-3, mode
+        assert rhs_ratio < 0.9, mode

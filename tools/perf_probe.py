@@ -29,8 +29,8 @@ ctx.set_columns(par, stat)
 ctx.set_forcing(f["precipitation_cm"][:T], f["wtd_idx"][:T], f["daylight"][:T], f["atm"][:T])
 ctx.set_output(30)
 ctx.set_noise_philox(1234, 0)
-if os.environ.get("HB_PROBE_FAST"):
-    ctx.set_fast_mode(True, True)          # fast mode (never the default): continuation + 3-colour Jacobian
+if os.environ.get("HB_PROBE_FAST"):        # fast mode (never the default): 1 = continuation + 3-colour Jacobian, 2 = + f32 closure
+    ctx.set_fast_mode(True, True, os.environ["HB_PROBE_FAST"] == "2")
 for rep in range(3):
     ctx.set_state(np.tile(g["ic"], (C, 1)))
     ctx.reset_counters()
