@@ -96,8 +96,11 @@ int  hb_spinup(hb_ctx *ctx, int max_iter, const double *nrnd0, const double *zwt
 int  hb_run(hb_ctx *ctx, int w0, int w1);
 
 /* Fast mode of hb_run: flags = OR of HB_FAST_* (hb_layout.h), 0 (default) = the reference's
- * arithmetic.  Departs from scipy common.py:63-134,268-455 and bdf.py:198-241 as the flag
- * comments say; hb_spinup and the hooks always run the parity path. */
+ * arithmetic.  Departs from scipy common.py:63-134,268-455 and bdf.py:198-241, and with
+ * HB_FAST_F32 from the double-precision closure of vrettas_fung.py:108-249 inside the Newton
+ * iteration, as the flag comments say; any flag also turns the divisions of the element-wise loops
+ * into multiplications by a refined reciprocal (1 ulp).  hb_spinup and the hooks always run the
+ * parity path. */
 int  hb_set_fast_mode(hb_ctx *ctx, int flags);
 
 /* Scheduling of hb_run.  Columns are independent, so the schedule never changes a
