@@ -310,7 +310,7 @@ def _both_jacobian_paths(work):
     return res
 
 
-def test_fused_jacobian_is_bit_identical():
+def test_fused_jacobian_is_bit_identical(tmp_path):
     """num_jac's first pass over the colour groups (SCIPY common.py:385-443) is made in ONE pass on
     the device: two closure evaluations per midpoint (own node perturbed / right neighbour
     perturbed) instead of one whole right-hand-side evaluation per group, the three rows of every
@@ -319,7 +319,8 @@ def test_fused_jacobian_is_bit_identical():
     (1) a mixed ensemble (both closures, all porosity profiles, lateral-flow sink on) with daily
     rows, (2) the same without the lateral-flow sink, (3) half-hourly rows with hydraulic lift at
     night (fused) and the root-uptake sink by day (evaluation per group), (4) failed attempts with
-    the damped noise field, (5) the spin-up kernel, (6) the default column (n = 2 closure)."""
+    the damped noise field, (5) the spin-up kernel, (6) the default column (n = 2 closure),
+    (7) the kernel variants of larger grids (701 and 1,001 nodes)."""
     n_cols, T = 192, 31
     table = synthetic_forcing(365).iloc[:T].reset_index(drop=True)
     base, cols = ensemble_columns(default_params(SITE), 4096, n_cols, mixed=True, perturb_theta=True)
@@ -398,6 +399,31 @@ def test_fused_jacobian_is_bit_identical():
     for u, v in zip(a5, b5):
         assert np.array_equal(u, v, equal_nan=True)
     assert col["par"][pack.P_N] == 2.0
+    # (7) the other kernel variants: 701 nodes (512 threads x 2 cells, run-time vector length, generic
+    # tridiagonal solver) and 1,001 nodes (512 x 3) under the stiff forcing
+    for depth, want_nx in ((3500.0, 701), (5000.0, 1001)):
+        site = fine_grid_site(str(tmp_path / ("site%d.json" % want_nx)), max_depth=depth)
+        tb = synthetic_forcing(365, stiff=True).iloc[:9].reset_index(drop=True)
+        bs, cs = ensemble_columns(default_params(site), 0, 24)
+        eg = pack.pack_ensemble(bs, tb, cs)
+        z = eg["x"]
+        assert z.size == want_nx
+        icg = np.tile(np.where(z > 800.0, z - 800.0, -0.35 * (800.0 - z) - 1.0), (24, 1))
+
+        def fine():
+            ctx, _ = open_ctx(eg)
+            ctx.set_noise_philox(SEED, 0)
+            ctx.set_output(4)
+            ctx.set_state(icg)
+            ctx.reset_counters()
+            ctx.run(0, 9)
+            out = (ctx.get_state(), ctx.get_wscal(), ctx.get_fields(), ctx.get_counters())
+            ctx.close()
+            return out
+
+        a7, b7 = _both_jacobian_paths(fine)
+        same(a7, b7, "nx = %d" % want_nx)
+        assert a7[3][:, pack.C_NJEV].sum() >= 24 * 8
 
 
 def test_short_noise_tape_fails_loudly():
