@@ -383,7 +383,21 @@ hb_ctx *hb_create(int device, int nx, int n_cols)
         gam[0] = 0.0;
         for (int k = 1; k <= 5; ++k) gam[k] = gam[k - 1] + 1.0 / k;
         for (int k = 0; k <= 5; ++k) { alp[k] = (1.0 - kappa[k]) * gam[k]; erc[k] = kappa[k] * gam[k] + 1.0 / (k + 1); }
-        if (cudaMemcpyToSymbol(hb::k_gamma, gam, sizeof(gam)) != cudaSuccess ||
+        // U of change_D, the operations and their order exactly as the device used to make them
+        // (and scipy's compute_R(order, 1), bdf.py:18-27, does)
+        double umat[36];
+        for (int k = 0; k < 6; ++k)
+            for (int j = 0; j < 6; ++j) {
+                volatile double ukj = 1.0;
+                for (int rr = 1; rr <= k; ++rr) {
+                    volatile double num = (double)(rr - 1) - 1.0 * (double)j;
+                    volatile double quo = num / (double)rr;
+                    ukj = (j == 0) ? ukj * 0.0 : ukj * quo;
+                }
+                umat[k * 6 + j] = ukj;
+            }
+        if (cudaMemcpyToSymbol(hb::k_U, umat, sizeof(umat)) != cudaSuccess ||
+            cudaMemcpyToSymbol(hb::k_gamma, gam, sizeof(gam)) != cudaSuccess ||
             cudaMemcpyToSymbol(hb::k_alpha, alp, sizeof(alp)) != cudaSuccess ||
             cudaMemcpyToSymbol(hb::k_error_const, erc, sizeof(erc)) != cudaSuccess) {
             fail("hb_create: constant upload failed"); delete ctx; return nullptr;

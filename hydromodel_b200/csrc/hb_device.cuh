@@ -182,6 +182,8 @@ struct Args {
 __constant__ double k_gamma[6];
 __constant__ double k_alpha[6];
 __constant__ double k_error_const[6];
+// U of change_D (bdf.py:18-33): U[k][j] = prod_{r=1..k} ((r-1) - j) / r, U[k][0] = (k == 0); row stride 6.
+__constant__ double k_U[36];
 
 }  // namespace hb
 

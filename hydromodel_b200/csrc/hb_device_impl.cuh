@@ -944,20 +944,23 @@ __device__ __noinline__ void change_D(const DevCtx &c, int order, double factor)
 {
     const int tid = threadIdx.x;
     const int q = order + 1;
-    double *ru = HB_XA(c, NV, X_RU);
-    __syncthreads();                       // previous readers of RU are done
+    double *ru = HB_XA(c, NV, X_RU), *rm = HB_XA(c, NV, X_RED);
+    __syncthreads();                       // previous readers of RU and of the reduction slots are done
+    // R[i][k] with `factor` (cumulative products down the rows, bdf.py:18-27), one entry per thread;
+    // U = R(factor = 1) does not depend on anything: host-made table k_U (same operations in the
+    // same order, hb_create).  Each entry of RU used to recompute its whole row of R and column of U.
     for (int e_ = tid; e_ < q * q; e_ += NT) {     // (NT may be smaller than 36: narrow A/B shapes)
+        const int i = e_ / q, k = e_ % q;
+        double Rik = 1.0;
+        for (int rr = 1; rr <= i; ++rr)
+            Rik *= (k == 0) ? 0.0 : ((double)(rr - 1) - factor * (double)k) / (double)rr;
+        rm[i * 6 + k] = Rik;
+    }
+    __syncthreads();
+    for (int e_ = tid; e_ < q * q; e_ += NT) {
         const int i = e_ / q, j = e_ % q;
         double acc = 0.0;
-        for (int k = 0; k < q; ++k) {
-            // R[i][k] with `factor`, U[k][j] with 1 (cumulative products down rows)
-            double Rik = 1.0, Ukj = 1.0;
-            for (int rr = 1; rr <= i; ++rr)
-                Rik *= (k == 0) ? 0.0 : ((double)(rr - 1) - factor * (double)k) / (double)rr;
-            for (int rr = 1; rr <= k; ++rr)
-                Ukj *= (j == 0) ? 0.0 : ((double)(rr - 1) - 1.0 * (double)j) / (double)rr;
-            acc += Rik * Ukj;
-        }
+        for (int k = 0; k < q; ++k) acc += rm[i * 6 + k] * k_U[k * 6 + j];
         ru[i * 6 + j] = acc;
     }
     __syncthreads();
