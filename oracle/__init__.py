@@ -104,6 +104,23 @@ def num_jac(x, groups, par, stat, psi, nrnd, precip, wtd, daylight=0, spinup=0, 
     return dl, d, du, fo
 
 
+def group_rows(x, groups, par, stat, psi, nrnd, precip, wtd, h, daylight=0, spinup=0, fused=False):
+    """rows[j, q] = f(psi + h on the colour group of column j)[j - 1 + q], q = 0..2: the numbers
+    num_jac reads (SCIPY common.py:385-443), by one evaluation per group (``fused=False``) or by
+    the one-pass scheme of the device's jac_fused (``fused=True``)."""
+    x, par, stat, psi, nrnd, h = _c(x), _c(par), _c(stat), _c(psi), _c(nrnd).copy(), _c(h)
+    groups = _c(groups, np.int32)
+    n = x.size
+    rows = np.empty((n, 3))
+    rc = lib().orc_group_rows_c(ct.c_int(n), _d(x), _i(groups), ct.c_int(int(groups.max()) + 1),
+                                _d(par), _d(stat), _d(psi), _d(nrnd), ct.c_double(precip),
+                                ct.c_int(int(wtd)), ct.c_int(int(daylight)), ct.c_int(int(spinup)),
+                                _d(h), ct.c_int(int(bool(fused))), _d(rows))
+    if rc != 0:
+        raise ValueError("orc_group_rows_c: the root-uptake sink is active (one evaluation per group only)")
+    return rows
+
+
 def solve_window(x, groups, par, stat, t0, t1, y0, nrnd, precip, wtd, daylight=0,
                  spinup=0, rtol=1e-3, atol=1e-3, max_acc=4096, atm=0.0):
     """One RichardsPDE.solve.  ``nrnd`` is damped in place on failure (Q4).

@@ -247,3 +247,58 @@ def test_halfhourly_daylight_windows_against_reference_tape(golden):
     assert n_day >= 20
     assert same.mean() >= 0.85
     assert np.median(errs) < 1e-3 and errs.max() < 5.0
+
+
+def test_one_pass_jacobian_differences_equal_the_evaluation_per_group(golden):
+    """The identity the device's jac_fused rests on, checked on the CPU: the rows j-1..j+1 of
+    f(y + h_g) that num_jac reads for column j (SCIPY common.py:385-443) are the same numbers,
+    bit for bit, whether f is evaluated once per colour group or assembled from two closure
+    evaluations per midpoint (own node perturbed / right neighbour perturbed) with the water table
+    of the lateral-flow sink estimated per group.  States: the spun-up profile and states of the
+    golden run, with perturbations from num_jac's own step rule up to ones that move cells across
+    saturation at the water table; flags: lateral flow on / off, hydraulic lift at night, surface
+    evaporation by day (root uptake off), spin-up; both closures; scipy's 5 colour groups and the
+    3 groups j mod 3."""
+    from hydromodel_b200.synthetic import default_params, ensemble_member
+    from helpers import SITE, forcing365
+    g = golden("windows_default.npz")
+    rng = np.random.default_rng(2024)
+    base = default_params(SITE)
+    table = forcing365()
+    cols = [pack.pack_column(base, table)]
+    for c in (3, 11):
+        p, _ = ensemble_member(base, c, 1024, mixed=True)
+        cols.append(pack.pack_column(p, table))
+    n_checked = 0
+    for ci, col in enumerate(cols):
+        nx = col["x"].size
+        for ng_variant in ("scipy", "mod3"):
+            grp = pack.fd_groups(nx)[0] if ng_variant == "scipy" else (np.arange(nx) % 3).astype(np.int32)
+            for w in (0, 40, 90):
+                y = g["y0"][w].copy() if nx == g["y0"].shape[1] else None
+                if y is None:
+                    continue
+                nr = g["n_rnd"][w]
+                for scale in (1.4901161193847656e-08, 1e-5, 3e-2, -4.0):
+                    sign = np.where(rng.random(nx) < 0.5, 1.0, -1.0)
+                    # (a negative scale is an absolute step in cm: moves midpoints across psi_sat)
+                    h = sign * (scale * np.maximum(1e-3, np.abs(y)) if scale > 0 else -scale)
+                    for flags, day, spin in ((1.0, 0, 0), (0.0, 0, 0), (5.0, 0, 0), (1.0, 1, 0), (1.0, 0, 1)):
+                        par = col["par"].copy()
+                        par[pack.P_FLAGS] = flags
+                        kw = dict(daylight=day, spinup=spin)
+                        a = oracle.group_rows(col["x"], grp, par, col["stat"], y, nr, 0.7, 170, h, fused=False, **kw)
+                        b = oracle.group_rows(col["x"], grp, par, col["stat"], y, nr, 0.7, 170, h, fused=True, **kw)
+                        assert np.array_equal(a.view(np.int64), b.view(np.int64)), (ci, ng_variant, w, scale, flags, day, spin)
+                        n_checked += 1
+    assert n_checked >= 250
+    # the absolute steps do move midpoints across saturation next to the water table
+    y = g["y0"][40]
+    psi_sat = cols[0]["par"][pack.P_PSI_SAT]
+    mid = 0.5 * (y[:-1] + y[1:])
+    assert np.sum(np.abs(mid - psi_sat) < 2.0) >= 1
+    # root uptake active: refused, as on the device (one evaluation per group there)
+    par = cols[0]["par"].copy(); par[pack.P_FLAGS] = 3.0
+    with pytest.raises(ValueError):
+        oracle.group_rows(cols[0]["x"], pack.fd_groups(401)[0], par, cols[0]["stat"], y, g["n_rnd"][40], 0.7, 170,
+                          1e-8 * np.abs(y), daylight=1, fused=True)
